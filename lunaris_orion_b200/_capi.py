@@ -1,0 +1,71 @@
+"""ctypes binding of include/lunaris_b200.h. Fails loudly when the library is missing (no fallback)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblunaris_b200.so")
+
+_ERRORS = {
+    2: "LUN_E_SHAPE: unsupported channel count / block size",
+    3: "LUN_E_TAPS: tap list empty or longer than 16",
+    4: "LUN_E_GRID: spatial grid is not a power of two",
+    5: "LUN_E_BOX: TMA box would exceed 256 elements",
+    6: "LUN_E_STATS", 7: "LUN_E_ALIGN: output channel stride/offset not 16-byte aligned",
+    8: "LUN_E_ATTR: cudaFuncSetAttribute failed", 9: "LUN_E_LAUNCH: kernel launch failed",
+    101: "LUN_E_DRIVER: cuTensorMapEncodeTiled unavailable", 102: "LUN_E_TMAP: tensor-map encode failed",
+    103: "LUN_E_TMAP: tensor-map encode failed (2d)",
+}
+
+
+class LunarisB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load liblunaris_b200.so once. Raises if it was not built (python -m lunaris_orion_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LunarisB200Error(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "lunaris_orion_b200 has no CPU / library fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+# name -> argtypes; every function returns int. Kept in sync with include/lunaris_b200.h
+# (tests/test_capi_symbols.py parses the header and checks this table against it).
+SIGNATURES = {
+    "lun_num_sms": [],
+    "lun_abi_version": [],
+    "lun_conv_taps_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                           c_int, c_int, c_int, c_int, c_int, c_int_p, c_int_p, c_int_p,
+                           c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_int, c_int, c_float, c_void_p, c_void_p],
+    "lun_wgrad_taps_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_int, c_int_p, c_int_p, c_int_p, c_void_p, c_void_p],
+}
+
+
+def _declare(l):
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+
+
+def check(rc, what):
+    if rc != 0:
+        raise LunarisB200Error(f"{what} failed with code {rc}: {_ERRORS.get(rc, 'unknown error')}")
+
+
+def int_array(values):
+    return (ctypes.c_int * len(values))(*values)

@@ -1,0 +1,50 @@
+// extern "C" surface of liblunaris_b200.so (declared in include/lunaris_b200.h).
+#include "../../include/lunaris_b200.h"
+#include "conv_gemm.cuh"
+
+namespace lun {
+int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, int nslabs, ConvGeom g,
+                      const float* bias, void* out, float* stats, cudaStream_t stream);
+int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int XB, int XH, int XW, WgradGeom g,
+                      float* dw, cudaStream_t stream);
+int num_sms();
+}  // namespace lun
+
+extern "C" {
+
+int lun_abi_version(void) { return 1; }
+int lun_num_sms(void) { return lun::num_sms(); }
+
+int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const void* w_packed, int nslabs, int Cout,
+                       int GB, int GH, int GW, int in_mul, int ntaps, const int* dy, const int* dx, const int* slab,
+                       const float* bias, void* out, int OH, int OW, int o_mul, int o_ph, int o_pw, int ldo,
+                       int o_coff, int flags, float slope, float* stats, void* stream) {
+  if (ntaps < 1 || ntaps > lun::kMaxTaps) return LUN_E_TAPS;
+  lun::ConvGeom g{};
+  g.GB = GB; g.GH = GH; g.GW = GW;
+  g.in_mul = in_mul;
+  g.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) { g.dy[t] = dy[t]; g.dx[t] = dx[t]; g.slab[t] = slab[t]; }
+  g.Cin = Cin; g.Cout = Cout;
+  g.block_n = Cout >= 256 && Cout % 256 == 0 ? 256 : Cout >= 128 && Cout % 128 == 0 ? 128 : Cout % 64 == 0 ? 64 : 32;
+  g.OH = OH; g.OW = OW; g.o_mul = o_mul; g.o_ph = o_ph; g.o_pw = o_pw; g.ldo = ldo; g.o_coff = o_coff;
+  g.flags = flags; g.slope = slope;
+  return lun::launch_conv_fprop(x, XB, XH, XW, w_packed, nslabs, g, bias, out, stats,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int lun_wgrad_taps_bf16(const void* dy, int YB, int YH, int YW, int Cout, int dy_mul, int dy_ph, int dy_pw,
+                        const void* x, int XB, int XH, int XW, int Cin, int in_mul, int GB, int GH, int GW,
+                        int ntaps, const int* tdy, const int* tdx, const int* slab, float* dw, void* stream) {
+  if (ntaps < 1 || ntaps > lun::kMaxTaps) return LUN_E_TAPS;
+  lun::WgradGeom g{};
+  g.GB = GB; g.GH = GH; g.GW = GW;
+  g.in_mul = in_mul;
+  g.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) { g.dy[t] = tdy[t]; g.dx[t] = tdx[t]; g.slab[t] = slab[t]; }
+  g.Cin = Cin; g.Cout = Cout;
+  g.dy_mul = dy_mul; g.dy_ph = dy_ph; g.dy_pw = dy_pw;
+  return lun::launch_conv_wgrad(dy, YB, YH, YW, x, XB, XH, XW, g, dw, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,355 @@
+// Implicit-GEMM convolution forward / data-gradient kernel for sm_100a.
+//
+//   D[128 pixels, block_n channels] = sum over taps t, channel chunks kc of  A_t,kc[128, 64] * B_t,kc[block_n, 64]^T
+//
+// * A tiles are fetched by TMA in tiled mode from the NHWC bf16 activation tensor viewed as a 4-D tensor
+//   {C, W, H, B}; the filter-tap shift is a coordinate offset and the halo is TMA out-of-bounds zero fill, so no
+//   im2col matrix ever exists. Strided convolutions use the tensor map's element strides.
+// * B tiles (weights packed [tap][Cout][Cin], K-major) are fetched by TMA from a 2-D map.
+// * Both land in shared memory in the 128-byte swizzle; one elected thread issues tcgen05.mma (M=128, N=block_n,
+//   K=16) with fp32 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+//   (TMEM -> registers -> bias / activation / BN batch statistics -> vectorised global stores).
+//
+// Replaces the reference's F.conv2d / conv_transpose2d call sites (lunar_evaluator.py:242,249,133,134,255;
+// lunar_generate.py:36,41,95-116,169-187) and their autograd data-gradients.
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+namespace lun {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct __align__(8) PipeBars {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvGeom g, const float* __restrict__ bias, void* __restrict__ out,
+                  float* __restrict__ stats) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int block_n = g.block_n;
+  const int b_bytes = block_n * 128;
+  const int stage_bytes = kABytes + b_bytes;
+  const int stages = g.stages;
+  PipeBars* bars = reinterpret_cast<PipeBars*>(smem + stages * stage_bytes);
+  float* s_stats = reinterpret_cast<float*>(bars + 1);  // [2 * Cout] when EPI_STATS
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_blocks = g.Cout / block_n;
+  const int m_tiles = g.ntb * g.nth * g.ntw;
+  const int total_tiles = m_tiles * n_blocks;
+  const int kchunks = g.Cin >> 6;
+  const int ksteps = g.ntaps * kchunks;
+  const uint32_t tmem_cols = (2 * block_n <= 32) ? 32u : (2 * block_n <= 64) ? 64u : (2 * block_n <= 128) ? 128u
+                             : (2 * block_n <= 256) ? 256u : 512u;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tfull[i], 1);
+      mbar_init(&bars->tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (g.flags & EPI_STATS) {
+    for (int i = threadIdx.x; i < 2 * g.Cout; i += kThreads) s_stats[i] = 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % n_blocks;
+        int m = tile / n_blocks;
+        const int tw = m % g.ntw;
+        m /= g.ntw;
+        const int th = m % g.nth;
+        const int tb = m / g.nth;
+        const int w0 = tw * g.TW * g.in_mul, h0 = th * g.TH * g.in_mul, b0 = tb * g.TB;
+        for (int t = 0; t < g.ntaps; ++t) {
+          const int cw = w0 + g.dx[t], ch = h0 + g.dy[t];
+          const int wrow = g.slab[t] * g.Cout + n_blk * block_n;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&bars->empty[s], ph ^ 1);
+            uint8_t* sa = smem + s * stage_bytes;
+            mbar_expect_tx(&bars->full[s], stage_bytes);
+            tma_load_4d(sa, &tmA, &bars->full[s], kc * 64, cw, ch, b0);
+            tma_load_2d(sa + kABytes, &tmB, &bars->full[s], kc * 64, wrow);
+            if (++s == stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, block_n, false, false);
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t pacc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->tempty[acc], pacc ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * block_n;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&bars->full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint64_t adesc = make_smem_desc_sw128(sa, 0, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 bf16 (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+          }
+          umma_commit(&bars->empty[s]);
+          if (ks == ksteps - 1) umma_commit(&bars->tfull[acc]);
+        }
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;      // accumulator row == pixel index inside the tile
+    const bool do_bias = g.flags & EPI_BIAS, do_leaky = g.flags & EPI_LEAKY, do_stats = g.flags & EPI_STATS;
+    const bool out_f32 = g.flags & EPI_OUT_F32, do_tanh = g.flags & EPI_TANH;
+    int acc = 0;
+    uint32_t pacc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % n_blocks;
+      int m = tile / n_blocks;
+      const int tw = m % g.ntw;
+      m /= g.ntw;
+      const int th = m % g.nth;
+      const int tb = m / g.nth;
+      const int lw = row % g.TW, lh = (row / g.TW) % g.TH, lb = row / (g.TW * g.TH);
+      const int gb = tb * g.TB + lb, gh = th * g.TH + lh, gw = tw * g.TW + lw;
+      const bool valid = gb < g.GB;
+      const size_t pix = (static_cast<size_t>(gb) * g.OH + (gh * g.o_mul + g.o_ph)) * g.OW + (gw * g.o_mul + g.o_pw);
+      const size_t obase = pix * g.ldo + g.o_coff + n_blk * block_n;
+
+      mbar_wait(&bars->tfull[acc], pacc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * block_n;
+      for (int c0 = 0; c0 < block_n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+        const int nb = n_blk * block_n + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (do_bias) x += __ldg(bias + nb + j);
+          if (do_leaky) x = x > 0.f ? x : x * g.slope;
+          if (do_tanh) x = tanhf(x);
+          v[j] = x;
+        }
+        if (out_f32) {
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+          uint32_t p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+          }
+          if (do_stats) {
+            // statistics of what was stored (bf16-rounded), as the reference's batch_norm sees them
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&p[j]);
+              v[2 * j] = __low2float(b2);
+              v[2 * j + 1] = __high2float(b2);
+            }
+          }
+        }
+        if (do_stats) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            s1[j] = valid ? v[j] : 0.f;
+            s2[j] = s1[j] * s1[j];
+          }
+          // transpose-reduce across the 32 lanes (rows): 31 shuffles per statistic, lane j ends with column j
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = lane & off;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send1 = upper ? s1[i] : s1[i + off];
+              const float keep1 = upper ? s1[i + off] : s1[i];
+              s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+              const float send2 = upper ? s2[i] : s2[i + off];
+              const float keep2 = upper ? s2[i + off] : s2[i];
+              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            }
+          }
+          atomicAdd(&s_stats[nb + lane], s1[0]);
+          atomicAdd(&s_stats[g.Cout + nb + lane], s2[0]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+    if (do_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < 2 * g.Cout; i += 128) atomicAdd(stats + i, s_stats[i]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 4-D bf16 NHWC activation map {C, W, H, B}; box = {64, bw, bh, bb} elements traversed with strides {1, es, es, 1}.
+int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b,
+                   int estride) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return 101;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
+  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 102;
+}
+
+// 2-D bf16 row-major matrix map {cols, rows}; box = {64, box_rows}.
+int make_tmap_2d(CUtensorMap* m, const void* base, long rows, long cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return 101;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 103;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// Split an output grid into 128-pixel tiles; returns false if the grid cannot be tiled.
+bool tile_grid(int GB, int GH, int GW, int pixels, int* TB, int* TH, int* TW) {
+  if (!pow2(GW) || !pow2(GH)) return false;
+  *TW = GW < pixels ? GW : pixels;
+  int rest = pixels / *TW;
+  *TH = GH < rest ? GH : rest;
+  *TB = rest / *TH;
+  return true;
+}
+
+// x: NHWC bf16 [XB, XH, XW, Cin]; wpk: [nslabs][Cout][Cin] bf16; out: [*, OH, OW, ldo]
+int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, int nslabs, ConvGeom g,
+                      const float* bias, void* out, float* stats, cudaStream_t stream) {
+  if (g.Cin % 64 != 0 || g.block_n % 32 != 0 || g.block_n > 256 || g.Cout % g.block_n != 0) return 2;
+  if (g.ntaps < 1 || g.ntaps > kMaxTaps) return 3;
+  if (!tile_grid(g.GB, g.GH, g.GW, 128, &g.TB, &g.TH, &g.TW)) return 4;
+  g.ntw = g.GW / g.TW;
+  g.nth = g.GH / g.TH;
+  g.ntb = (g.GB + g.TB - 1) / g.TB;
+  if (g.TW * g.in_mul > 256 || g.TH * g.in_mul > 256 || g.TB > 256) return 5;
+  if ((g.flags & EPI_STATS) && g.Cout > 1024) return 6;
+  if (!(g.flags & EPI_OUT_F32) && (g.ldo % 8 || g.o_coff % 8)) return 7;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_nhwc(&tmA, x, XB, XH, XW, g.Cin, g.TW * g.in_mul, g.TH * g.in_mul, g.TB, g.in_mul);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, wpk, (long)nslabs * g.Cout, g.Cin, g.block_n);
+  if (rc) return rc;
+
+  const int stage_bytes = kABytes + g.block_n * 128;
+  const int extra = (int)sizeof(PipeBars) + ((g.flags & EPI_STATS) ? 2 * g.Cout * 4 : 0) + 1024;
+  int stages = (227 * 1024 - extra) / stage_bytes;
+  if (stages > 8) stages = 8;
+  g.stages = stages;
+  const int smem_bytes = stages * stage_bytes + extra;
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    if (cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return 8;
+    configured = 227 * 1024;
+  }
+  const int total_tiles = g.ntb * g.nth * g.ntw * (g.Cout / g.block_n);
+  int grid = num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  conv_fprop_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, g, bias, out, stats);
+  return cudaGetLastError() == cudaSuccess ? 0 : 9;
+}
+
+}  // namespace lun

@@ -1,0 +1,53 @@
+// Shared host/device declarations for the tcgen05 implicit-GEMM kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lun {
+
+constexpr int kMaxTaps = 16;
+
+// Epilogue flags
+enum : int {
+  EPI_BIAS = 1,       // + bias[n] (fp32)
+  EPI_LEAKY = 2,      // leaky_relu(slope)
+  EPI_STATS = 4,      // per-channel sum / sum-of-squares of the stored (rounded) values -> stats[0:N], stats[N:2N]
+  EPI_OUT_F32 = 8,    // store fp32 instead of bf16
+  EPI_TANH = 16,      // tanh after bias
+};
+
+// Implicit-GEMM geometry. GEMM-M enumerates an output grid [GB, GH, GW] in tiles of [TB, TH, TW] (TB*TH*TW == 128).
+// For tap t the A operand row of grid point (b, h, w) is the input pixel (b, h*in_mul + dy[t], w*in_mul + dx[t]),
+// zero outside the image (TMA out-of-bounds fill); the B operand is weight slab slab[t] = [Cout][Cin] (K-major).
+struct ConvGeom {
+  int GB, GH, GW;
+  int TB, TH, TW;
+  int ntb, nth, ntw;
+  int in_mul;
+  int ntaps;
+  int dy[kMaxTaps], dx[kMaxTaps], slab[kMaxTaps];
+  int Cin, Cout, block_n;
+  int stages;
+  // output tensor [*, OH, OW, ldo]; grid point (b,h,w) -> pixel (b, h*o_mul + o_ph, w*o_mul + o_pw), channel o_coff + n
+  int OH, OW, o_mul, o_ph, o_pw, ldo, o_coff;
+  int flags;
+  float slope;
+};
+
+// Weight-gradient geometry: dW[slab[t]][co][ci] += sum over grid points of dY[b,h,w,co] * X[b, h*in_mul+dy, w*in_mul+dx, ci]
+struct WgradGeom {
+  int GB, GH, GW;      // dY grid (pixels reduced over)
+  int TB, TH, TW;      // k-chunk tile (TB*TH*TW == 64 pixels)
+  int ntb, nth, ntw;
+  int in_mul;
+  int ntaps;
+  int dy[kMaxTaps], dx[kMaxTaps], slab[kMaxTaps];
+  int Cin, Cout;       // Cout = GEMM M (blocks of 128), Cin = GEMM N (blocks of block_n)
+  int block_n;
+  int stages;
+  int splits;          // split-K factor (k-chunks are dealt round-robin to splits)
+  int dy_mul, dy_ph, dy_pw;  // dY pixel = grid*dy_mul + phase  (transposed-conv phases)
+};
+
+}  // namespace lun

@@ -1,0 +1,244 @@
+// Weight-gradient kernel for sm_100a:  dW[slab][co][ci] += sum_pixels dY[pixel, co] * X[shift_tap(pixel), ci]
+//
+// The reduction (GEMM-K) dimension is the pixel index, so with NHWC activations both operands are "MN-major":
+// a TMA box of {64 channels, 64 pixels} lands in shared memory as 64 rows of 128 bytes (128-byte swizzle), which is
+// exactly the canonical MN-major SWIZZLE_128B UMMA layout (LBO = 8 KB between 64-channel atoms, SBO = 1 KB between
+// 8-pixel groups). tcgen05.mma M=128 (Cout block), N=block_n (Cin block), K=16 pixels, fp32 accumulators in TMEM.
+// Work unit = (Cout block, Cin block, tap, K-split); units are dealt round-robin to a persistent grid and each
+// finishes with vectorised fp32 red.global.add into the packed gradient buffer (zeroed by the caller).
+//
+// Replaces the autograd weight-gradients of the reference's conv2d / conv_transpose2d call sites
+// (lunar_evaluator.py:249,134,255; lunar_generate.py:36,41,95-116,169-187).
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+namespace lun {
+
+int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b,
+                   int estride);
+int num_sms();
+bool tile_grid(int GB, int GH, int GW, int pixels, int* TB, int* TH, int* TW);
+
+constexpr int kWgThreads = 192;
+constexpr int kWgABytes = 128 * 128;  // 64 pixels x 128 channels bf16
+
+struct __align__(8) WgBars {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const WgradGeom g, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int block_n = g.block_n;
+  const int b_bytes = block_n * 128;
+  const int stage_bytes = kWgABytes + b_bytes;
+  const int stages = g.stages;
+  WgBars* bars = reinterpret_cast<WgBars*>(smem + stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (g.Cout + 127) / 128;
+  const int n_blocks = (g.Cin + block_n - 1) / block_n;
+  const int tiles = m_blocks * n_blocks * g.ntaps;
+  const int units = tiles * g.splits;
+  const int chunks = g.ntb * g.nth * g.ntw;  // 64-pixel k-chunks
+  const uint32_t tmem_cols = (2 * block_n <= 64) ? 64u : (2 * block_n <= 128) ? 128u : (2 * block_n <= 256) ? 256u : 512u;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tfull[i], 1);
+      mbar_init(&bars->tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // unit -> (split, tap, n_blk, m_blk); chunk range of a split: [c_lo, c_hi)
+  auto chunk_lo = [&](int split) { return static_cast<int>(static_cast<long long>(chunks) * split / g.splits); };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = u / tiles;
+        int t = u % tiles;
+        const int m_blk = t % m_blocks;
+        t /= m_blocks;
+        const int n_blk = t % n_blocks;
+        const int tap = t / n_blocks;
+        const int c_lo = chunk_lo(split), c_hi = chunk_lo(split + 1);
+        for (int c = c_lo; c < c_hi; ++c) {
+          const int tw = c % g.ntw;
+          const int th = (c / g.ntw) % g.nth;
+          const int tb = c / (g.ntw * g.nth);
+          mbar_wait(&bars->empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          mbar_expect_tx(&bars->full[s], stage_bytes);
+          const int yw = tw * g.TW * g.dy_mul + g.dy_pw, yh = th * g.TH * g.dy_mul + g.dy_ph;
+          tma_load_4d(sa, &tmDY, &bars->full[s], m_blk * 128, yw, yh, tb * g.TB);
+          tma_load_4d(sa + 8192, &tmDY, &bars->full[s], m_blk * 128 + 64, yw, yh, tb * g.TB);
+          const int xw = tw * g.TW * g.in_mul + g.dx[tap], xh = th * g.TH * g.in_mul + g.dy[tap];
+          for (int j = 0; j < block_n / 64; ++j)
+            tma_load_4d(sa + kWgABytes + j * 8192, &tmX, &bars->full[s], n_blk * block_n + j * 64, xw, xh,
+                        tb * g.TB);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(128, block_n, true, true);
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t pacc = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int split = u / tiles;
+      const int nk = chunk_lo(split + 1) - chunk_lo(split);
+      if (nk == 0) continue;
+      mbar_wait(&bars->tempty[acc], pacc ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * block_n;
+      for (int ks = 0; ks < nk; ++ks) {
+        mbar_wait(&bars->full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          // MN-major, 128B swizzle: LBO = 8192 (next 64-channel atom), SBO = 1024 (next 8-pixel group)
+          const uint64_t adesc = make_smem_desc_sw128(sa, 8192, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + kWgABytes, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 pixels = 16 rows of 128 B = 2048 B -> +128 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + 128 * k, bdesc + 128 * k, idesc, (ks | k) != 0);
+          }
+          umma_commit(&bars->empty[s]);
+          if (ks == nk - 1) umma_commit(&bars->tfull[acc]);
+        }
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t pacc = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int split = u / tiles;
+      const int nk = chunk_lo(split + 1) - chunk_lo(split);
+      if (nk == 0) continue;
+      int t = u % tiles;
+      const int m_blk = t % m_blocks;
+      t /= m_blocks;
+      const int n_blk = t % n_blocks;
+      const int tap = t / n_blocks;
+      const int co = m_blk * 128 + row;
+      float* dst_row = dw + (static_cast<size_t>(g.slab[tap]) * g.Cout + co) * g.Cin + n_blk * block_n;
+      mbar_wait(&bars->tfull[acc], pacc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * block_n;
+      for (int c0 = 0; c0 < block_n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        if (co < g.Cout) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int ci = n_blk * block_n + c0 + 4 * j;
+            if (ci < g.Cin)
+              red_add_v4(dst_row + c0 + 4 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// dy: NHWC bf16 [YB, YH, YW, Cout]; x: NHWC bf16 [XB, XH, XW, Cin]; dw: fp32 [nslabs][Cout][Cin], pre-zeroed.
+int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int XB, int XH, int XW, WgradGeom g,
+                      float* dw, cudaStream_t stream) {
+  if (g.ntaps < 1 || g.ntaps > kMaxTaps) return 3;
+  if (g.Cin % 4 != 0 || g.Cout % 8 != 0 || g.Cin % 8 != 0) return 2;
+  if (!tile_grid(g.GB, g.GH, g.GW, 64, &g.TB, &g.TH, &g.TW)) return 4;
+  g.ntw = g.GW / g.TW;
+  g.nth = g.GH / g.TH;
+  g.ntb = (g.GB + g.TB - 1) / g.TB;
+  int bn = g.Cin >= 256 ? 256 : g.Cin >= 128 ? 128 : 64;
+  g.block_n = bn;
+  if (g.TW * g.in_mul > 256 || g.TH * g.in_mul > 256 || g.TW * g.dy_mul > 256 || g.TH * g.dy_mul > 256) return 5;
+
+  CUtensorMap tmDY, tmX;
+  int rc = make_tmap_nhwc(&tmDY, dy, YB, YH, YW, g.Cout, g.TW * g.dy_mul, g.TH * g.dy_mul, g.TB, g.dy_mul);
+  if (rc) return rc;
+  rc = make_tmap_nhwc(&tmX, x, XB, XH, XW, g.Cin, g.TW * g.in_mul, g.TH * g.in_mul, g.TB, g.in_mul);
+  if (rc) return rc;
+
+  const int stage_bytes = kWgABytes + bn * 128;
+  const int extra = (int)sizeof(WgBars) + 1024;
+  int stages = (227 * 1024 - extra) / stage_bytes;
+  if (stages > 8) stages = 8;
+  g.stages = stages;
+  const int smem_bytes = stages * stage_bytes + extra;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return 8;
+    configured = true;
+  }
+  const int m_blocks = (g.Cout + 127) / 128, n_blocks = (g.Cin + bn - 1) / bn;
+  const int tiles = m_blocks * n_blocks * g.ntaps;
+  const int chunks = g.ntb * g.nth * g.ntw;
+  // enough K-splits for ~4 units per SM, but keep at least 8 k-chunks per unit
+  int splits = (4 * num_sms() + tiles - 1) / tiles;
+  if (splits > chunks / 8) splits = chunks / 8;
+  if (splits < 1) splits = 1;
+  g.splits = splits;
+  int grid = num_sms();
+  if (grid > tiles * splits) grid = tiles * splits;
+  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, g, dw);
+  return cudaGetLastError() == cudaSuccess ? 0 : 9;
+}
+
+}  // namespace lun

@@ -1,0 +1,217 @@
+"""Host-side launchers: torch tensors in, C-ABI calls out (include/lunaris_b200.h).
+
+Activations are NHWC bf16 contiguous tensors; packed weights are bf16 [slab][Cout][Cin]. Tap lists translate the
+reference's conv2d / conv_transpose2d / linear call sites (lunar_generate.py, lunar_evaluator.py) and their
+gradients into the implicit-GEMM form the kernels execute.
+"""
+import torch
+
+from . import _capi
+from ._capi import check, int_array
+
+EPI_BIAS, EPI_LEAKY, EPI_STATS, EPI_OUT_F32, EPI_TANH = 1, 2, 4, 8, 16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _nhwc(t):
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ weight packing
+def pack_conv_weight(w):
+    """[Cout,Cin,kh,kw] fp32 -> bf16 [kh*kw][Cout][Cin] (forward operand)."""
+    co, ci, kh, kw = w.shape
+    return w.detach().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16).contiguous()
+
+
+def pack_conv_weight_dgrad(w):
+    """[Cout,Cin,kh,kw] -> bf16 [kh*kw][Cin][Cout] (data-gradient operand)."""
+    co, ci, kh, kw = w.shape
+    return w.detach().permute(2, 3, 1, 0).reshape(kh * kw, ci, co).to(torch.bfloat16).contiguous()
+
+
+def pack_convT_weight(w):
+    """ConvTranspose2d weight [Cin,Cout,kh,kw] -> bf16 [kh*kw][Cout][Cin] (forward operand)."""
+    ci, co, kh, kw = w.shape
+    return w.detach().permute(2, 3, 1, 0).reshape(kh * kw, co, ci).to(torch.bfloat16).contiguous()
+
+
+def pack_convT_weight_dgrad(w):
+    """ConvTranspose2d weight [Cin,Cout,kh,kw] -> bf16 [kh*kw][Cin][Cout] (data-gradient operand)."""
+    ci, co, kh, kw = w.shape
+    return w.detach().permute(2, 3, 0, 1).reshape(kh * kw, ci, co).to(torch.bfloat16).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ raw launchers
+def conv_taps(x, w_packed, cout, grid, in_mul, taps, out, out_hw, o_mul=1, o_ph=0, o_pw=0, o_coff=0, bias=None,
+              flags=0, slope=0.2, stats=None):
+    """out[b, h*o_mul+o_ph, w*o_mul+o_pw, o_coff+n] = epi(sum_t x[b, h*in_mul+dy_t, w*in_mul+dx_t, :] . w[slab_t][n])."""
+    _nhwc(x)
+    XB, XH, XW, cin = x.shape
+    GB, GH, GW = grid
+    dy = int_array([t[0] for t in taps])
+    dx = int_array([t[1] for t in taps])
+    sl = int_array([t[2] for t in taps])
+    if bias is not None:
+        flags |= EPI_BIAS
+        assert bias.dtype == torch.float32
+    if stats is not None:
+        flags |= EPI_STATS
+        assert stats.dtype == torch.float32 and stats.numel() == 2 * cout
+    assert w_packed.dtype == torch.bfloat16 and w_packed.shape[1] == cout and w_packed.shape[2] == cin
+    assert out.dtype == (torch.float32 if flags & EPI_OUT_F32 else torch.bfloat16)
+    rc = _capi.lib().lun_conv_taps_bf16(
+        x.data_ptr(), XB, XH, XW, cin, w_packed.data_ptr(), w_packed.shape[0], cout, GB, GH, GW, in_mul, len(taps),
+        dy, dx, sl, _ptr(bias), out.data_ptr(), out_hw[0], out_hw[1], o_mul, o_ph, o_pw, out.shape[-1], o_coff,
+        flags, slope, _ptr(stats), _stream())
+    check(rc, "lun_conv_taps_bf16")
+    return out
+
+
+def wgrad_taps(dy, x, grid, taps, dw, dy_mul=1, dy_ph=0, dy_pw=0, in_mul=1):
+    """dw[slab_t][m][n] += sum_grid dy[b, h*dy_mul+dy_ph, w*dy_mul+dy_pw, m] * x[b, h*in_mul+dy_t, w*in_mul+dx_t, n]."""
+    _nhwc(dy), _nhwc(x)
+    YB, YH, YW, cm = dy.shape
+    XB, XH, XW, cn = x.shape
+    GB, GH, GW = grid
+    assert dw.dtype == torch.float32 and dw.shape[1] == cm and dw.shape[2] == cn and dw.is_contiguous()
+    tdy = int_array([t[0] for t in taps])
+    tdx = int_array([t[1] for t in taps])
+    sl = int_array([t[2] for t in taps])
+    rc = _capi.lib().lun_wgrad_taps_bf16(dy.data_ptr(), YB, YH, YW, cm, dy_mul, dy_ph, dy_pw, x.data_ptr(), XB, XH, XW,
+                                         cn, in_mul, GB, GH, GW, len(taps), tdy, tdx, sl, dw.data_ptr(), _stream())
+    check(rc, "lun_wgrad_taps_bf16")
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------ conv2d
+def _conv_taps_list(k, pad):
+    return [(kh - pad, kw - pad, kh * k + kw) for kh in range(k) for kw in range(k)]
+
+
+def conv2d_fprop(x, w_packed, k, stride, pad, bias=None, act_leaky=False, stats=None, out=None, out_f32=False,
+                 slope=0.2):
+    """F.conv2d on NHWC bf16 (lunar_evaluator.py:242; lunar_generate.py:36,95). Optional fused bias, LeakyReLU and
+    per-channel batch statistics (sum, sum of squares) for the BatchNorm that follows in the reference."""
+    B, H, W, _ = x.shape
+    cout = w_packed.shape[1]
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    if out is None:
+        out = torch.empty(B, OH, OW, cout, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    flags = (EPI_LEAKY if act_leaky else 0) | (EPI_OUT_F32 if out_f32 else 0)
+    return conv_taps(x, w_packed, cout, (B, OH, OW), stride, _conv_taps_list(k, pad), out, (OH, OW), bias=bias,
+                     flags=flags, slope=slope, stats=stats)
+
+
+def conv2d_dgrad(dy, w_packed_dgrad, k, stride, pad, in_hw, out=None):
+    """Gradient of F.conv2d w.r.t. its input. dy: [B,OH,OW,Cout] bf16; returns [B,H,W,Cin] bf16."""
+    B, OH, OW, _ = dy.shape
+    H, W = in_hw
+    cin = w_packed_dgrad.shape[1]
+    if out is None:
+        out = torch.empty(B, H, W, cin, device=dy.device, dtype=torch.bfloat16)
+    if stride == 1:
+        taps = [(pad - kh, pad - kw, kh * k + kw) for kh in range(k) for kw in range(k)]
+        return conv_taps(dy, w_packed_dgrad, cin, (B, H, W), 1, taps, out, (H, W))
+    assert stride == 2 and H % 2 == 0 and W % 2 == 0
+    # input pixel ih = 2*j + ph receives dy[oh] * w[kh] with ih = 2*oh - pad + kh  ->  oh = j + (ph + pad - kh) / 2
+    for ph in range(2):
+        for pw in range(2):
+            taps = []
+            for kh in range(k):
+                if (ph + pad - kh) % 2:
+                    continue
+                for kw in range(k):
+                    if (pw + pad - kw) % 2:
+                        continue
+                    taps.append(((ph + pad - kh) // 2, (pw + pad - kw) // 2, kh * k + kw))
+            conv_taps(dy, w_packed_dgrad, cin, (B, H // 2, W // 2), 1, taps, out, (H, W), o_mul=2, o_ph=ph, o_pw=pw)
+    return out
+
+
+def conv2d_wgrad(dy, x, k, stride, pad):
+    """Gradient of F.conv2d w.r.t. its weight, returned in the reference layout [Cout,Cin,kh,kw] fp32."""
+    B, OH, OW, cout = dy.shape
+    cin = x.shape[-1]
+    dw = torch.zeros(k * k, cout, cin, device=dy.device, dtype=torch.float32)
+    wgrad_taps(dy, x, (B, OH, OW), _conv_taps_list(k, pad), dw, in_mul=stride)
+    return dw.view(k, k, cout, cin).permute(2, 3, 0, 1)
+
+
+# ------------------------------------------------------------------------------------------------ conv_transpose2d (k4 s2 p1)
+def _convT_phase_taps(ph, pw):
+    # output row oh = 2*j + ph gathers input rows ih with oh = 2*ih - 1 + kh
+    rows = [(0, 1), (-1, 3)] if ph == 0 else [(1, 0), (0, 2)]   # (ih - j, kh)
+    cols = [(0, 1), (-1, 3)] if pw == 0 else [(1, 0), (0, 2)]
+    return [(dh, dw, kh * 4 + kw) for dh, kh in rows for dw, kw in cols]
+
+
+def convT4x4s2_fprop(x, w_packed, bias=None, out=None):
+    """F.conv_transpose2d(k=4, s=2, p=1) as four output-phase 2x2-tap sub-convolutions (lunar_generate.py:169-187)."""
+    B, H, W, _ = x.shape
+    cout = w_packed.shape[1]
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, cout, device=x.device, dtype=torch.bfloat16)
+    for ph in range(2):
+        for pw in range(2):
+            conv_taps(x, w_packed, cout, (B, H, W), 1, _convT_phase_taps(ph, pw), out, (2 * H, 2 * W), o_mul=2,
+                      o_ph=ph, o_pw=pw, bias=bias)
+    return out
+
+
+def convT4x4s2_dgrad(dy, w_packed_dgrad, out=None):
+    """Gradient of conv_transpose2d(k4,s2,p1) w.r.t. its input = stride-2 4x4 convolution of dy."""
+    B, OH, OW, _ = dy.shape
+    cin = w_packed_dgrad.shape[1]
+    H, W = OH // 2, OW // 2
+    if out is None:
+        out = torch.empty(B, H, W, cin, device=dy.device, dtype=torch.bfloat16)
+    taps = [(kh - 1, kw - 1, kh * 4 + kw) for kh in range(4) for kw in range(4)]
+    return conv_taps(dy, w_packed_dgrad, cin, (B, H, W), 2, taps, out, (H, W))
+
+
+def convT4x4s2_wgrad(dy, x):
+    """Gradient w.r.t. the ConvTranspose2d weight, reference layout [Cin,Cout,4,4] fp32."""
+    B, H, W, cin = x.shape
+    cout = dy.shape[-1]
+    dw = torch.zeros(16, cin, cout, device=dy.device, dtype=torch.float32)
+    taps = [(kh - 1, kw - 1, kh * 4 + kw) for kh in range(4) for kw in range(4)]
+    wgrad_taps(x, dy, (B, H, W), taps, dw, in_mul=2)
+    return dw.view(4, 4, cin, cout).permute(2, 3, 0, 1)
+
+
+# ------------------------------------------------------------------------------------------------ linear
+def linear_fprop(x, w_bf16, bias=None, out_f32=True):
+    """nn.Linear on [B,K] bf16 with weight [N,K] bf16 (lunar_generate.py:124-125,165)."""
+    B, K = x.shape
+    N = w_bf16.shape[0]
+    out = torch.empty(B, N, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    conv_taps(x.view(B, 1, 1, K), w_bf16.view(1, N, K), N, (B, 1, 1), 1, [(0, 0, 0)], out.view(B, 1, 1, N), (1, 1),
+              bias=bias, flags=EPI_OUT_F32 if out_f32 else 0)
+    return out
+
+
+def linear_dgrad(dy, w_t_bf16):
+    """dx = dy @ W with W^T packed as [K,N] bf16; dy [B,N] bf16 -> [B,K] bf16."""
+    B, N = dy.shape
+    K = w_t_bf16.shape[0]
+    out = torch.empty(B, K, device=dy.device, dtype=torch.bfloat16)
+    conv_taps(dy.view(B, 1, 1, N), w_t_bf16.view(1, K, N), K, (B, 1, 1), 1, [(0, 0, 0)], out.view(B, 1, 1, K), (1, 1))
+    return out
+
+
+def linear_wgrad(dy, x):
+    """dW[N,K] = dy^T @ x, fp32."""
+    B, N = dy.shape
+    K = x.shape[1]
+    dw = torch.zeros(1, N, K, device=dy.device, dtype=torch.float32)
+    wgrad_taps(dy.view(B, 1, 1, N), x.view(B, 1, 1, K), (B, 1, 1), [(0, 0, 0)], dw)
+    return dw.view(N, K)
