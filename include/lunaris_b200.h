@@ -28,7 +28,6 @@ extern "C" {
 #define LUN_EPI_LEAKY 2
 #define LUN_EPI_STATS 4
 #define LUN_EPI_OUT_F32 8
-#define LUN_EPI_TANH 16
 
 /* Library / device probe: returns the SM count of the current device (148 on B200), <=0 on error. */
 int lun_num_sms(void);
@@ -53,6 +52,71 @@ int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const voi
 int lun_wgrad_taps_bf16(const void* dy, int YB, int YH, int YW, int Cout, int dy_mul, int dy_ph, int dy_pw,
                         const void* x, int XB, int XH, int XW, int Cin, int in_mul, int GB, int GH, int GW,
                         int ntaps, const int* tdy, const int* tdx, const int* slab, float* dw, void* stream);
+
+/* ---- Bandwidth-bound Teacher kernels (NHWC bf16 [B, HW, C]; C % 8 == 0) -------------------------------------- */
+
+/* Per-channel sum and sum of squares of x[P, C] accumulated into stats[2*C] (caller zeroes).
+ * Reference: the batch statistics nn.BatchNorm2d computes in training mode (lunar_evaluator.py:74,81,88,95,102). */
+int lun_channel_stats_bf16(const void* x, long P, int C, float* stats, void* stream);
+
+/* BatchNorm2d training-mode finalize: stats -> (scale, shift) with y = x*scale + shift, (mean, rstd) for backward,
+ * and n_updates momentum updates of running_mean / running_var (unbiased) / num_batches_tracked.
+ * n_updates reproduces the reference's 1x (no_grad pass), 1x or 2x (checkpoint recompute) updates, SURVEY.md 0.4.
+ * Reference: lunar_evaluator.py:244,251,256 (nn.BatchNorm2d inside ExpertBlock), :74-102. */
+int lun_bn_finalize(const float* stats, double n, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, int n_updates, float momentum, float eps,
+                    float* scale, float* shift, float* mean, float* rstd, int C, void* stream);
+
+/* y = act( ls * drop( drop2d( x*scale + shift ) ) + identity' )  with every optional stage switched by a null
+ * pointer / zero probability: mask2d [B,C] is the Dropout2d keep-mask (values 0 or 1/(1-p)); drop_p>0 applies
+ * elementwise dropout from the counter-based RNG (seed); ls [C] is ExpertBlock.layer_scale; identity [B,HW,C] is the
+ * residual (optionally through its own BN affine id_scale/id_shift) followed by leaky_relu(slope); pool [B,C]
+ * receives the per-image channel sums of y (AdaptiveAvgPool2d numerators).
+ * Reference: lunar_evaluator.py:244-245,251-253 (BN + Dropout2d), :264 (layer_scale), :275 (residual + leaky_relu),
+ * :97 (Dropout), :355,366,378,390,435 (pooling). */
+int lun_affine_fwd_bf16(const void* x, const float* scale, const float* shift, const float* mask2d, const float* ls,
+                        const void* identity, const float* id_scale, const float* id_shift, void* y, float* pool,
+                        unsigned long long seed, float drop_p, int B, int HW, int C, float slope, void* stream);
+
+/* Backward of the ExpertBlock tail, pass 1: dpre = dout * leaky'(out) (dout may be the broadcast pooled gradient
+ * gpool[B,C]); accumulates t1[c] = sum dpre*mask2d, t2[c] = sum dpre*mask2d*xhat (xhat from bn_in, mean, rstd).
+ * Reference: autograd of lunar_evaluator.py:263-264,275. */
+int lun_block_bwd_reduce_bf16(const void* dout, const float* gpool, const void* out, const void* bn_in,
+                              const float* mean, const float* rstd, const float* mask2d, void* dpre, float* t1,
+                              float* t2, int B, int HW, int C, float slope_out, void* stream);
+
+/* Pass 2: dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) * leaky'(bn_in), g = dpre*ls*mask2d; dbias[c] += sum dz.
+ * dz is the gradient at the conv output feeding conv dgrad / wgrad. */
+int lun_block_bwd_apply_bf16(const void* dpre, const float* gpool, const void* out, const void* bn_in,
+                             const float* mean, const float* rstd, const float* gamma, const float* ls,
+                             const float* mask2d, const float* t1, const float* t2, void* dz, float* dbias, int B,
+                             int HW, int C, float slope_out, float slope_a, void* stream);
+
+/* Block-local attention exactly as the reference executes it (chunk-index scatter, lunar_evaluator.py:203-216):
+ * att_small[b, i, :] for i < N/32 + 31 is the only non-zero part of the pre-proj tensor. qkv: [B, N, 3C] with
+ * channel order [3][heads][hd]. drop_p is attn_drop (:212). */
+int lun_attn_ref_rows_bf16(const void* qkv, void* att_small, int B, int N, int C, int heads, int nq_pad,
+                           unsigned long long seed, float drop_p, void* stream);
+
+/* y[b,p,:] = proj_drop( p < nq ? proj_small[b,p,:] : bias )  (lunar_evaluator.py:224-225 on the mostly-zero input). */
+int lun_proj_expand_bf16(const void* proj_small, const float* bias, void* y, int B, int HW, int C, int nq, int nq_pad,
+                         unsigned long long seed, float drop_p, void* stream);
+
+/* Backward of proj_drop: dpo = mask*dh2; dbias[c] += column sums; rows p < nq gathered into dpo_small. */
+int lun_proj_bwd_gather_bf16(const void* dh2, void* dpo_small, float* dbias, int B, int HW, int C, int nq, int nq_pad,
+                             unsigned long long seed, float drop_p, void* stream);
+
+/* PixelArtFeatureExtractor.conv1: conv3x3 3->32 + LeakyReLU on NCHW fp32 images -> NHWC bf16, + BN statistics
+ * (lunar_evaluator.py:71-75). w is the reference layout [32,3,3,3] fp32. */
+int lun_fe_conv1(const float* x_nchw, const float* w, const float* bias, void* y, float* stats, int B, int H, int W,
+                 float slope, void* stream);
+
+/* The three branches (depthwise 3x3 / 5x5 / 3x3 -> pointwise 32->64 -> LeakyReLU) written into the 192-channel concat
+ * buffer; BN of conv1 (scale, shift) is applied on load (lunar_evaluator.py:77-96,106-110).
+ * dw_w/dw_b/pw_w/pw_b: host arrays of 3 device pointers (edge, color, detail), reference layouts, fp32. */
+int lun_fe_branches(const void* y0, const float* scale, const float* shift, const float* const* dw_w,
+                    const float* const* dw_b, const float* const* pw_w, const float* const* pw_b, void* cat, int B,
+                    int H, int W, float slope, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,8 @@ def lib():
 
 
 c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+c_long, c_double, c_u64 = ctypes.c_long, ctypes.c_double, ctypes.c_ulonglong
+c_pp = ctypes.POINTER(ctypes.c_void_p)
 c_int_p = ctypes.POINTER(ctypes.c_int)
 
 # name -> argtypes; every function returns int. Kept in sync with include/lunaris_b200.h
@@ -52,6 +54,24 @@ SIGNATURES = {
     "lun_wgrad_taps_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int_p, c_int_p, c_int_p, c_void_p, c_void_p],
+    "lun_channel_stats_bf16": [c_void_p, c_long, c_int, c_void_p, c_void_p],
+    "lun_bn_finalize": [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
+                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "lun_affine_fwd_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_u64, c_float, c_int, c_int, c_int, c_float, c_void_p],
+    "lun_block_bwd_reduce_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],
+    "lun_block_bwd_apply_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                 c_float, c_void_p],
+    "lun_attn_ref_rows_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_float, c_void_p],
+    "lun_proj_expand_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_float,
+                             c_void_p],
+    "lun_proj_bwd_gather_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_float,
+                                 c_void_p],
+    "lun_fe_conv1": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],
+    "lun_fe_branches": [c_void_p, c_void_p, c_void_p, c_pp, c_pp, c_pp, c_pp, c_void_p, c_int, c_int, c_int, c_float,
+                        c_void_p],
 }
 
 

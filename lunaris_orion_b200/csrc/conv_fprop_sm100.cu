@@ -21,7 +21,7 @@ namespace lun {
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
-struct __align__(8) PipeBars {
+struct __align__(16) PipeBars {
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t tfull[2];
@@ -32,7 +32,7 @@ struct __align__(8) PipeBars {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const ConvGeom g, const float* __restrict__ bias, void* __restrict__ out,
+                  const __grid_constant__ CUtensorMap tmO, const ConvGeom g, const float* __restrict__ bias, void* __restrict__ out,
                   float* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -40,8 +40,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int b_bytes = block_n * 128;
   const int stage_bytes = kABytes + b_bytes;
   const int stages = g.stages;
-  PipeBars* bars = reinterpret_cast<PipeBars*>(smem + stages * stage_bytes);
-  float* s_stats = reinterpret_cast<float*>(bars + 1);  // [2 * Cout] when EPI_STATS
+  uint8_t* s_stage = smem + stages * stage_bytes;  // 16 KB output staging tile (128 rows x 128 B, swizzled)
+  PipeBars* bars = reinterpret_cast<PipeBars*>(s_stage + kABytes);
+  float* s_bias = reinterpret_cast<float*>(bars + 1);   // [Cout]
+  float* s_stats = s_bias + g.Cout;                     // [2 * Cout] when EPI_STATS
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -57,6 +59,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (g.flags & EPI_TMA_STORE) prefetch_tmap(&tmO);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
@@ -67,6 +70,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < g.Cout; i += kThreads) s_bias[i] = (g.flags & EPI_BIAS) ? bias[i] : 0.f;
   if (g.flags & EPI_STATS) {
     for (int i = threadIdx.x; i < 2 * g.Cout; i += kThreads) s_stats[i] = 0.f;
   }
@@ -141,10 +145,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;      // accumulator row == pixel index inside the tile
-    const bool do_bias = g.flags & EPI_BIAS, do_leaky = g.flags & EPI_LEAKY, do_stats = g.flags & EPI_STATS;
-    const bool out_f32 = g.flags & EPI_OUT_F32, do_tanh = g.flags & EPI_TANH;
+    const bool do_stats = g.flags & EPI_STATS, out_f32 = g.flags & EPI_OUT_F32, tma_out = g.flags & EPI_TMA_STORE;
+    const float slope = (g.flags & EPI_LEAKY) ? g.slope : 1.f;
+    const bool epi_leader = threadIdx.x == 64;
+    const uint32_t stg_row = smem_u32(s_stage) + row * 128;
     int acc = 0;
     uint32_t pacc = 0;
+    bool store_pending = false;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_blk = tile % n_blocks;
       int m = tile / n_blocks;
@@ -164,16 +171,25 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int c0 = 0; c0 < block_n; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
-        tmem_ld_wait();
-        float v[32];
         const int nb = n_blk * block_n + c0;
+        float bv[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(s_bias + nb + 4 * j);
+          bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+        }
+        tmem_ld_wait();
+        if (c0 + 32 >= block_n) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+        }
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (do_bias) x += __ldg(bias + nb + j);
-          if (do_leaky) x = x > 0.f ? x : x * g.slope;
-          if (do_tanh) x = tanhf(x);
-          v[j] = x;
+          const float x = __uint_as_float(r[j]) + bv[j];
+          v[j] = fmaxf(x, 0.f) + slope * fminf(x, 0.f);
         }
         if (out_f32) {
           if (valid) {
@@ -185,7 +201,36 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint32_t p[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          if (valid) {
+          if (tma_out) {
+            const int half = (c0 >> 5) & 1;
+            if (half == 0) {
+              // the staging tile is reused: wait until the previous TMA store has finished reading it
+              if (store_pending) {
+                if (epi_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t chunk = static_cast<uint32_t>((half * 4 + j) ^ (row & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + (chunk << 4)), "r"(p[4 * j]),
+                           "r"(p[4 * j + 1]), "r"(p[4 * j + 2]), "r"(p[4 * j + 3])
+                           : "memory");
+            }
+            if (half == 1) {
+              fence_proxy_async();
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (epi_leader) {
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                        &tmO),
+                    "r"(smem_u32(s_stage)), "r"(g.o_coff + nb - 32), "r"(tw * g.TW), "r"(th * g.TH), "r"(tb * g.TB)
+                    : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              store_pending = true;
+            }
+          } else if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + obase + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
@@ -194,9 +239,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // statistics of what was stored (bf16-rounded), as the reference's batch_norm sees them
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&p[j]);
-              v[2 * j] = __low2float(b2);
-              v[2 * j + 1] = __high2float(b2);
+              v[2 * j] = __uint_as_float(p[j] << 16);
+              v[2 * j + 1] = __uint_as_float(p[j] & 0xffff0000u);
             }
           }
         }
@@ -225,11 +269,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           atomicAdd(&s_stats[g.Cout + nb + lane], s2[0]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tempty[acc]);
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
+    if (store_pending && epi_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = threadIdx.x - 64; i < 2 * g.Cout; i += 128) atomicAdd(stats + i, s_stats[i]);
@@ -323,17 +365,28 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   g.nth = g.GH / g.TH;
   g.ntb = (g.GB + g.TB - 1) / g.TB;
   if (g.TW * g.in_mul > 256 || g.TH * g.in_mul > 256 || g.TB > 256) return 5;
-  if ((g.flags & EPI_STATS) && g.Cout > 1024) return 6;
+  if (g.Cout > 2048 && (g.flags & EPI_STATS)) return 6;
   if (!(g.flags & EPI_OUT_F32) && (g.ldo % 8 || g.o_coff % 8)) return 7;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
+  // coalesced asynchronous output path: bf16, dense pixel mapping, 64-channel boxes
+  if (!(g.flags & EPI_OUT_F32) && g.o_mul == 1 && g.block_n % 64 == 0)
+    g.flags |= EPI_TMA_STORE;
+  else
+    g.flags &= ~EPI_TMA_STORE;
   int rc = make_tmap_nhwc(&tmA, x, XB, XH, XW, g.Cin, g.TW * g.in_mul, g.TH * g.in_mul, g.TB, g.in_mul);
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, wpk, (long)nslabs * g.Cout, g.Cin, g.block_n);
   if (rc) return rc;
 
+  if (g.flags & EPI_TMA_STORE) {
+    rc = make_tmap_nhwc(&tmO, out, g.GB, g.OH, g.OW, g.ldo, g.TW, g.TH, g.TB, 1);
+    if (rc) return rc;
+  } else {
+    tmO = tmA;
+  }
   const int stage_bytes = kABytes + g.block_n * 128;
-  const int extra = (int)sizeof(PipeBars) + ((g.flags & EPI_STATS) ? 2 * g.Cout * 4 : 0) + 1024;
+  const int extra = kABytes + (int)sizeof(PipeBars) + g.Cout * 4 + ((g.flags & EPI_STATS) ? 2 * g.Cout * 4 : 0) + 1024;
   int stages = (227 * 1024 - extra) / stage_bytes;
   if (stages > 8) stages = 8;
   g.stages = stages;
@@ -348,7 +401,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   const int total_tiles = g.ntb * g.nth * g.ntw * (g.Cout / g.block_n);
   int grid = num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  conv_fprop_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, g, bias, out, stats);
+  conv_fprop_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmO, g, bias, out, stats);
   return cudaGetLastError() == cudaSuccess ? 0 : 9;
 }
 

@@ -14,7 +14,7 @@ enum : int {
   EPI_LEAKY = 2,      // leaky_relu(slope)
   EPI_STATS = 4,      // per-channel sum / sum-of-squares of the stored (rounded) values -> stats[0:N], stats[N:2N]
   EPI_OUT_F32 = 8,    // store fp32 instead of bf16
-  EPI_TANH = 16,      // tanh after bias
+  EPI_TMA_STORE = 32, // (set by the launcher) bf16 output leaves through a swizzled smem tile + TMA store
 };
 
 // Implicit-GEMM geometry. GEMM-M enumerates an output grid [GB, GH, GW] in tiles of [TB, TH, TW] (TB*TH*TW == 128).

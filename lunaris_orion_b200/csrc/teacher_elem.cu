@@ -1,0 +1,551 @@
+// Bandwidth-bound kernels of the Teacher (LunarMoETeacher) path: BatchNorm finalize / apply, the ExpertBlock residual
+// epilogue (forward and backward), channel statistics, the as-executed local attention rows and the proj expansion.
+// All tensors are NHWC bf16 [B, HW, C]; a thread owns 8 consecutive channels (16-byte accesses), a block owns a
+// set of pixel lanes so per-channel reductions finish in shared memory with one atomic per channel per block.
+//
+// Reference call sites: lunar_evaluator.py:71-103 (FE BatchNorm/LeakyReLU/Dropout), :189-227 (attention),
+// :241-258 (ExpertBlock conv->LeakyReLU->BN->Dropout2d, layer_scale), :260-275 (residual + leaky_relu).
+#include "../../include/lunaris_b200.h"
+#include "elem_common.cuh"
+
+namespace lun {
+
+constexpr int kEThreads = 256;
+
+struct ChanGeom {
+  int cg;      // channel groups of 8
+  int lanes;   // pixel lanes per block
+  __device__ __forceinline__ ChanGeom(int C) : cg(C >> 3), lanes(kEThreads / (C >> 3)) {}
+};
+
+// sums[k][c] partial per thread -> block reduce -> atomicAdd(dst_k[c]). NS = number of statistics.
+template <int NS>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NS][8], float* smem, int C, int lane_px, int cgi,
+                                                     bool active, float* const (&dst)[NS]) {
+  // smem layout [lanes][NS][C]
+  const ChanGeom g(C);
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) smem[(lane_px * NS + k) * C + cgi * 8 + j] = acc[k][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NS * C; i += kEThreads) {
+    float s = 0.f;
+    for (int l = 0; l < g.lanes; ++l) s += smem[l * NS * C + i];
+    const int k = i / C, c = i % C;
+    atomicAdd(dst[k] + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- channel statistics
+__global__ void __launch_bounds__(kEThreads) channel_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats,
+                                                                  long P, int C) {
+  extern __shared__ float smem[];
+  const ChanGeom g(C);
+  const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
+  const bool active = lane_px < g.lanes;
+  float acc[2][8] = {};
+  if (active) {
+    for (long p = (long)blockIdx.x * g.lanes + lane_px; p < P; p += (long)gridDim.x * g.lanes) {
+      float v[8];
+      load8(x + p * C + cgi * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += v[j];
+        acc[1][j] += v[j] * v[j];
+      }
+    }
+  }
+  float* const dst[2] = {stats, stats + C};
+  block_channel_reduce<2>(acc, smem, C, lane_px, cgi, active, dst);
+}
+
+// ------------------------------------------------------------------------------------------- BN finalize
+// stats = [sum | sumsq] over n elements per channel. Produces the normalisation affine (scale, shift), keeps
+// mean / rstd for backward and applies the running-statistics update `n_updates` times (momentum, unbiased var).
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, double n, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean,
+                                   float* __restrict__ rvar, long long* __restrict__ nbt, int n_updates,
+                                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = stats[c] / n;
+  double var = stats[C + c] / n - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mean * sc;
+  mean_out[c] = (float)mean;
+  rstd_out[c] = rstd;
+  if (n_updates > 0 && rmean) {
+    const float var_u = (float)(n > 1 ? var * n / (n - 1) : var);
+    float rm = rmean[c], rv = rvar[c];
+    for (int i = 0; i < n_updates; ++i) {
+      rm = (1.f - momentum) * rm + momentum * (float)mean;
+      rv = (1.f - momentum) * rv + momentum * var_u;
+    }
+    rmean[c] = rm;
+    rvar[c] = rv;
+    if (c == 0 && nbt) *nbt += n_updates;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- affine forward
+struct AffineArgs {
+  const bf16* x;          // [B,HW,C]
+  const float* scale;     // [C]
+  const float* shift;     // [C]
+  const float* m2;        // [B,C] Dropout2d keep-mask (0 or 1/(1-p), bf16-representable) or null
+  const float* ls;        // [C] layer scale or null
+  const bf16* idn;        // identity [B,HW,C] or null
+  const float* id_scale;  // [C] affine on the identity (shortcut BatchNorm) or null
+  const float* id_shift;
+  bf16* y;
+  float* pool;            // [B,C] sums over HW of the (unrounded) result or null
+  unsigned long long seed;
+  unsigned int thresh16;  // elementwise dropout threshold (0 = off)
+  float drop_scale;
+  int B, HW, C;
+  float slope;            // leaky slope applied after the residual add when idn != null
+};
+
+__global__ void __launch_bounds__(kEThreads) affine_fwd_kernel(const AffineArgs a) {
+  extern __shared__ float smem[];
+  const ChanGeom g(a.C);
+  const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
+  const bool active = lane_px < g.lanes;
+  const int b = blockIdx.y;
+  const int c0 = cgi * 8;
+  float sc[8], sh[8], m2[8], ls[8], isc[8], ish[8];
+  float acc[1][8] = {};
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = a.scale ? a.scale[c0 + j] : 1.f;
+      sh[j] = a.shift ? a.shift[c0 + j] : 0.f;
+      m2[j] = a.m2 ? a.m2[(size_t)b * a.C + c0 + j] : 1.f;
+      ls[j] = a.ls ? a.ls[c0 + j] : 1.f;
+      isc[j] = a.id_scale ? a.id_scale[c0 + j] : 1.f;
+      ish[j] = a.id_scale ? a.id_shift[c0 + j] : 0.f;
+    }
+    for (int p = blockIdx.x * g.lanes + lane_px; p < a.HW; p += gridDim.x * g.lanes) {
+      const size_t off = ((size_t)b * a.HW + p) * a.C + c0;
+      float v[8];
+      load8(a.x + off, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = rbf(v[j] * sc[j] + sh[j]);
+        if (a.m2) v[j] = rbf(v[j] * m2[j]);
+      }
+      if (a.thresh16) {
+        bool keep[8];
+        drop_keep8(a.seed, off >> 3, a.thresh16, keep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = keep[j] ? rbf(v[j] * a.drop_scale) : 0.f;
+      }
+      if (a.ls) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= ls[j];
+      }
+      if (a.idn) {
+        float iv[8];
+        load8(a.idn + off, iv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float id = a.id_scale ? rbf(iv[j] * isc[j] + ish[j]) : iv[j];
+          const float s = v[j] + id;
+          v[j] = s > 0.f ? s : s * a.slope;
+        }
+      }
+      store8(a.y + off, v);
+      if (a.pool) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+      }
+    }
+  }
+  if (a.pool) {
+    float* const dst[1] = {a.pool + (size_t)b * a.C};
+    block_channel_reduce<1>(acc, smem, a.C, lane_px, cgi, active, dst);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- block epilogue backward
+struct BlkBwdArgs {
+  const bf16* dout;     // [B,HW,C] upstream gradient, or null when gpool is used
+  const float* gpool;   // [B,C] gradient of the HW-sum pooled features (dout = gpool broadcast), or null
+  const bf16* out;      // [B,HW,C] block output (sign gives the leaky_relu derivative), or null when slope_out == 1
+  const bf16* a;        // [B,HW,C] BatchNorm input (post-LeakyReLU conv output)
+  const float* mean;    // [C]
+  const float* rstd;    // [C]
+  const float* m2;      // [B,C] or null
+  bf16* dpre;           // [B,HW,C] gradient w.r.t. the pre-activation sum (= gradient of the identity branch)
+  float* t1;            // [C] sum dpre*m2
+  float* t2;            // [C] sum dpre*m2*xhat
+  int B, HW, C;
+  float slope_out;
+};
+
+__global__ void __launch_bounds__(kEThreads) blk_bwd_reduce_kernel(const BlkBwdArgs a) {
+  extern __shared__ float smem[];
+  const ChanGeom g(a.C);
+  const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
+  const bool active = lane_px < g.lanes;
+  const int b = blockIdx.y, c0 = cgi * 8;
+  float acc[2][8] = {};
+  if (active) {
+    float mean[8], rstd[8], m2[8], gp[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = a.mean[c0 + j];
+      rstd[j] = a.rstd[c0 + j];
+      m2[j] = a.m2 ? a.m2[(size_t)b * a.C + c0 + j] : 1.f;
+      gp[j] = a.gpool ? a.gpool[(size_t)b * a.C + c0 + j] : 0.f;
+    }
+    for (int p = blockIdx.x * g.lanes + lane_px; p < a.HW; p += gridDim.x * g.lanes) {
+      const size_t off = ((size_t)b * a.HW + p) * a.C + c0;
+      float d[8], av[8];
+      if (a.dout) load8(a.dout + off, d);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = gp[j];
+      }
+      if (a.out) {
+        float o[8];
+        load8(a.out + off, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : d[j] * a.slope_out;
+      }
+      if (a.dpre) store8(a.dpre + off, d);
+      load8(a.a + off, av);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dm = (a.dpre ? rbf(d[j]) : d[j]) * m2[j];
+        acc[0][j] += dm;
+        acc[1][j] += dm * (av[j] - mean[j]) * rstd[j];
+      }
+    }
+  }
+  float* const dst[2] = {a.t1, a.t2};
+  block_channel_reduce<2>(acc, smem, a.C, lane_px, cgi, active, dst);
+}
+
+struct BlkBwdApplyArgs {
+  const bf16* dpre;     // [B,HW,C] (or null with gpool/out as in the reduce pass)
+  const float* gpool;
+  const bf16* out;
+  const bf16* a;        // BN input
+  const float* mean; const float* rstd; const float* gamma;
+  const float* ls;      // [C] or null (1)
+  const float* m2;      // [B,C] or null
+  const float* t1; const float* t2;   // from the reduce pass
+  bf16* dz;             // [B,HW,C] gradient w.r.t. the conv output (before LeakyReLU)
+  float* dbias;         // [C] column sums of dz (conv bias gradient) or null
+  int B, HW, C;
+  float slope_out;      // leaky slope of the block output (used when dpre == null)
+  float slope_a;        // leaky slope between conv and BN (1 = none)
+  float inv_n;          // 1 / (B*HW)
+};
+
+__global__ void __launch_bounds__(kEThreads) blk_bwd_apply_kernel(const BlkBwdApplyArgs a) {
+  extern __shared__ float smem[];
+  const ChanGeom g(a.C);
+  const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
+  const bool active = lane_px < g.lanes;
+  const int b = blockIdx.y, c0 = cgi * 8;
+  float acc[1][8] = {};
+  if (active) {
+    float mean[8], rstd[8], k0[8], s1[8], s2[8], gp[8], gm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float ls = a.ls ? a.ls[c] : 1.f;
+      mean[j] = a.mean[c];
+      rstd[j] = a.rstd[c];
+      gm[j] = ls * (a.m2 ? a.m2[(size_t)b * a.C + c] : 1.f);   // g = dpre * gm
+      s1[j] = ls * a.t1[c] * a.inv_n;
+      s2[j] = ls * a.t2[c] * a.inv_n;
+      k0[j] = a.gamma[c] * rstd[j];
+      gp[j] = a.gpool ? a.gpool[(size_t)b * a.C + c] : 0.f;
+    }
+    for (int p = blockIdx.x * g.lanes + lane_px; p < a.HW; p += gridDim.x * g.lanes) {
+      const size_t off = ((size_t)b * a.HW + p) * a.C + c0;
+      float d[8], av[8];
+      if (a.dpre) load8(a.dpre + off, d);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = gp[j];
+        if (a.out) {
+          float o[8];
+          load8(a.out + off, o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : d[j] * a.slope_out;
+        }
+      }
+      load8(a.a + off, av);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (av[j] - mean[j]) * rstd[j];
+        float z = k0[j] * (d[j] * gm[j] - s1[j] - xh * s2[j]);
+        if (av[j] <= 0.f) z *= a.slope_a;
+        d[j] = z;
+      }
+      store8(a.dz + off, d);
+      if (a.dbias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[0][j] += rbf(d[j]);
+      }
+    }
+  }
+  if (a.dbias) {
+    float* const dst[1] = {a.dbias};
+    block_channel_reduce<1>(acc, smem, a.C, lane_px, cgi, active, dst);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- attention (as executed)
+// One warp per (image b, query slot i < nq, head). Query slot i < nc-1 is token 32*i (row 0 of chunk i); slots
+// nc-1 .. nc+30 are the 32 tokens of the last chunk. Output row i of att_small is what the reference leaves at
+// position i of `out` before proj (lunar_evaluator.py:203-216). Lane j owns key j of the chunk.
+__global__ void __launch_bounds__(256) attn_ref_rows_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ att,
+                                                             int B, int N, int C, int heads, int nq_pad,
+                                                             unsigned long long seed, unsigned int thresh16,
+                                                             float drop_scale) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nc = N / 32;
+  const int nq = nc + 31;
+  const int total = B * nq * heads;
+  if (warp >= total) return;
+  const int h = warp % heads;
+  const int i = (warp / heads) % nq;
+  const int b = warp / (heads * nq);
+  const int hd = C / heads;
+  const int chunk = i < nc - 1 ? i : nc - 1;
+  const int qtok = i < nc - 1 ? 32 * i : 32 * (nc - 1) + (i - (nc - 1));
+  const size_t row = (size_t)3 * C;
+  const bf16* qp = qkv + ((size_t)b * N + qtok) * row + h * hd;
+  const bf16* kp = qkv + ((size_t)b * N + 32 * chunk + lane) * row + C + h * hd;
+  const bf16* vbase = qkv + ((size_t)b * N + 32 * chunk) * row + 2 * C + h * hd;
+  float s = 0.f;
+  for (int d = 0; d < hd; d += 8) {
+    float qv[8], kv[8];
+    load8(qp + d, qv);
+    load8(kp + d, kv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += qv[j] * kv[j];
+  }
+  // reference dtype flow under bf16 autocast: scores and the scale product are bf16, softmax is fp32
+  s = rbf(rbf(s) * rbf(rsqrtf((float)hd)));
+  float m = s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float e = __expf(s - m);
+  const float sum = warp_sum(e);
+  float p = e / sum;
+  if (thresh16) {
+    const unsigned long long idx = ((unsigned long long)warp << 5) + lane;
+    p = drop_keep1(seed, idx, thresh16) ? p * drop_scale : 0.f;
+  }
+  p = rbf(p);
+  for (int d0 = 0; d0 < hd; d0 += 32) {
+    const int d = d0 + lane;
+    float o = 0.f;
+    if (d < hd) {
+      for (int j = 0; j < 32; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p, j);
+        o += pj * __bfloat162float(vbase[(size_t)j * row + d]);
+      }
+      att[((size_t)b * nq_pad + i) * C + h * hd + d] = __float2bfloat16_rn(o);
+    } else {
+      for (int j = 0; j < 32; ++j) __shfl_sync(0xffffffffu, p, j);
+    }
+  }
+}
+
+// h2[b,p,:] = dropout( p < nq ? proj_small[b,p,:] : bf16(bias) )   (lunar_evaluator.py:224-225)
+__global__ void __launch_bounds__(kEThreads) proj_expand_kernel(const bf16* __restrict__ small,
+                                                               const float* __restrict__ bias,
+                                                               bf16* __restrict__ y, int B, int HW, int C, int nq,
+                                                               int nq_pad, unsigned long long seed,
+                                                               unsigned int thresh16, float drop_scale) {
+  const ChanGeom g(C);
+  const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
+  if (lane_px >= g.lanes) return;
+  const int b = blockIdx.y, c0 = cgi * 8;
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = rbf(bias[c0 + j]);
+  for (int p = blockIdx.x * g.lanes + lane_px; p < HW; p += gridDim.x * g.lanes) {
+    const size_t off = ((size_t)b * HW + p) * C + c0;
+    float v[8];
+    if (p < nq) load8(small + ((size_t)b * nq_pad + p) * C + c0, v);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = bv[j];
+    }
+    if (thresh16) {
+      bool keep[8];
+      drop_keep8(seed, off >> 3, thresh16, keep);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = keep[j] ? rbf(v[j] * drop_scale) : 0.f;
+    }
+    store8(y + off, v);
+  }
+}
+
+// Backward of proj_drop + what proj's gradients need: dpo = mask * dh2; column sums of dpo (proj bias gradient);
+// the first nq rows of every image (the only rows where proj's input is non-zero) gathered into dpo_small.
+__global__ void __launch_bounds__(kEThreads) proj_bwd_gather_kernel(const bf16* __restrict__ dh2,
+                                                                   bf16* __restrict__ dpo_small,
+                                                                   float* __restrict__ dbias, int B, int HW, int C,
+                                                                   int nq, int nq_pad, unsigned long long seed,
+                                                                   unsigned int thresh16, float drop_scale) {
+  extern __shared__ float smem[];
+  const ChanGeom g(C);
+  const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
+  const bool active = lane_px < g.lanes;
+  const int b = blockIdx.y, c0 = cgi * 8;
+  float acc[1][8] = {};
+  if (active) {
+    for (int p = blockIdx.x * g.lanes + lane_px; p < HW; p += gridDim.x * g.lanes) {
+      const size_t off = ((size_t)b * HW + p) * C + c0;
+      float v[8];
+      load8(dh2 + off, v);
+      if (thresh16) {
+        bool keep[8];
+        drop_keep8(seed, off >> 3, thresh16, keep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = keep[j] ? rbf(v[j] * drop_scale) : 0.f;
+      }
+      if (p < nq) store8(dpo_small + ((size_t)b * nq_pad + p) * C + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+    }
+  }
+  float* const dst[1] = {dbias};
+  block_channel_reduce<1>(acc, smem, C, lane_px, cgi, active, dst);
+}
+
+static int elem_blocks_per_image(int HW, int C, int B) {
+  const int lanes = kEThreads / (C / 8);
+  int per = (HW + lanes - 1) / lanes;
+  // aim for ~8 blocks per SM overall
+  int want = (148 * 8 + B - 1) / B;
+  if (want < 1) want = 1;
+  return per < want ? per : want;
+}
+static bool chan_ok(int C) { return C % 8 == 0 && C / 8 <= kEThreads && C >= 8; }
+
+}  // namespace lun
+
+using namespace lun;
+
+extern "C" {
+
+int lun_channel_stats_bf16(const void* x, long P, int C, float* stats, void* stream) {
+  if (!chan_ok(C)) return LUN_E_SHAPE;
+  const int lanes = kEThreads / (C / 8);
+  long blocks = (P + lanes - 1) / lanes;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  channel_stats_kernel<<<(int)blocks, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)x, stats, P, C);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_bn_finalize(const float* stats, double n, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, int n_updates, float momentum, float eps,
+                    float* scale, float* shift, float* mean, float* rstd, int C, void* stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, n, gamma, beta, running_mean,
+                                                                       running_var, num_batches_tracked, n_updates,
+                                                                       momentum, eps, scale, shift, mean, rstd, C);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_affine_fwd_bf16(const void* x, const float* scale, const float* shift, const float* mask2d, const float* ls,
+                        const void* identity, const float* id_scale, const float* id_shift, void* y, float* pool,
+                        unsigned long long seed, float drop_p, int B, int HW, int C, float slope, void* stream) {
+  if (!chan_ok(C)) return LUN_E_SHAPE;
+  AffineArgs a;
+  a.x = (const bf16*)x; a.scale = scale; a.shift = shift; a.m2 = mask2d; a.ls = ls; a.idn = (const bf16*)identity;
+  a.id_scale = id_scale; a.id_shift = id_shift; a.y = (bf16*)y; a.pool = pool; a.seed = seed;
+  a.thresh16 = drop_p > 0.f ? (unsigned int)(drop_p * 65536.f + 0.5f) : 0u;
+  a.drop_scale = drop_p > 0.f ? __bfloat162float(__float2bfloat16_rn(1.f / (1.f - drop_p))) : 1.f;
+  a.B = B; a.HW = HW; a.C = C; a.slope = slope;
+  const int lanes = kEThreads / (C / 8);
+  dim3 grid(elem_blocks_per_image(HW, C, B), B);
+  affine_fwd_kernel<<<grid, kEThreads, pool ? lanes * C * sizeof(float) : 0, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_block_bwd_reduce_bf16(const void* dout, const float* gpool, const void* out, const void* bn_in,
+                              const float* mean, const float* rstd, const float* mask2d, void* dpre, float* t1,
+                              float* t2, int B, int HW, int C, float slope_out, void* stream) {
+  if (!chan_ok(C)) return LUN_E_SHAPE;
+  BlkBwdArgs a;
+  a.dout = (const bf16*)dout; a.gpool = gpool; a.out = (const bf16*)out; a.a = (const bf16*)bn_in; a.mean = mean;
+  a.rstd = rstd; a.m2 = mask2d; a.dpre = (bf16*)dpre; a.t1 = t1; a.t2 = t2; a.B = B; a.HW = HW; a.C = C;
+  a.slope_out = slope_out;
+  const int lanes = kEThreads / (C / 8);
+  dim3 grid(elem_blocks_per_image(HW, C, B), B);
+  blk_bwd_reduce_kernel<<<grid, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_block_bwd_apply_bf16(const void* dpre, const float* gpool, const void* out, const void* bn_in,
+                             const float* mean, const float* rstd, const float* gamma, const float* ls,
+                             const float* mask2d, const float* t1, const float* t2, void* dz, float* dbias, int B,
+                             int HW, int C, float slope_out, float slope_a, void* stream) {
+  if (!chan_ok(C)) return LUN_E_SHAPE;
+  BlkBwdApplyArgs a;
+  a.dpre = (const bf16*)dpre; a.gpool = gpool; a.out = (const bf16*)out; a.a = (const bf16*)bn_in; a.mean = mean;
+  a.rstd = rstd; a.gamma = gamma; a.ls = ls; a.m2 = mask2d; a.t1 = t1; a.t2 = t2; a.dz = (bf16*)dz;
+  a.dbias = dbias; a.B = B; a.HW = HW; a.C = C; a.slope_out = slope_out; a.slope_a = slope_a;
+  a.inv_n = 1.f / ((float)B * (float)HW);
+  const int lanes = kEThreads / (C / 8);
+  dim3 grid(elem_blocks_per_image(HW, C, B), B);
+  blk_bwd_apply_kernel<<<grid, kEThreads, dbias ? lanes * C * sizeof(float) : 0, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_attn_ref_rows_bf16(const void* qkv, void* att_small, int B, int N, int C, int heads, int nq_pad,
+                           unsigned long long seed, float drop_p, void* stream) {
+  if (N % 32 || C % heads || (C / heads) % 8) return LUN_E_SHAPE;
+  const int nq = N / 32 + 31;
+  if (nq_pad < nq) return LUN_E_SHAPE;
+  const long warps = (long)B * nq * heads;
+  const unsigned int th = drop_p > 0.f ? (unsigned int)(drop_p * 65536.f + 0.5f) : 0u;
+  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  attn_ref_rows_kernel<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)qkv, (bf16*)att_small, B, N, C, heads, nq_pad, seed, th, ds);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_proj_expand_bf16(const void* proj_small, const float* bias, void* y, int B, int HW, int C, int nq, int nq_pad,
+                         unsigned long long seed, float drop_p, void* stream) {
+  if (!chan_ok(C)) return LUN_E_SHAPE;
+  const unsigned int th = drop_p > 0.f ? (unsigned int)(drop_p * 65536.f + 0.5f) : 0u;
+  const float ds = drop_p > 0.f ? __bfloat162float(__float2bfloat16_rn(1.f / (1.f - drop_p))) : 1.f;
+  dim3 grid(elem_blocks_per_image(HW, C, B), B);
+  proj_expand_kernel<<<grid, kEThreads, 0, (cudaStream_t)stream>>>((const bf16*)proj_small, bias, (bf16*)y, B, HW, C,
+                                                                  nq, nq_pad, seed, th, ds);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_proj_bwd_gather_bf16(const void* dh2, void* dpo_small, float* dbias, int B, int HW, int C, int nq, int nq_pad,
+                             unsigned long long seed, float drop_p, void* stream) {
+  if (!chan_ok(C)) return LUN_E_SHAPE;
+  const unsigned int th = drop_p > 0.f ? (unsigned int)(drop_p * 65536.f + 0.5f) : 0u;
+  const float ds = drop_p > 0.f ? __bfloat162float(__float2bfloat16_rn(1.f / (1.f - drop_p))) : 1.f;
+  const int lanes = kEThreads / (C / 8);
+  dim3 grid(elem_blocks_per_image(HW, C, B), B);
+  proj_bwd_gather_kernel<<<grid, kEThreads, lanes * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)dh2, (bf16*)dpo_small, dbias, B, HW, C, nq, nq_pad, seed, th, ds);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+}  // extern "C"

@@ -1,0 +1,516 @@
+"""Drop-in for the reference's `lunar_evaluator` module (MeryylleA/Lunaris-Orion lunar_evaluator.py:57-462).
+
+Same classes, constructor signatures, sub-module tree (=> identical state_dict keys, parameter order and init-RNG
+consumption) and forward contract as the reference, but `forward` runs the B200-native kernels of
+liblunaris_b200.so on NHWC bf16 tensors. Semantics are the reference's AS EXECUTED:
+
+  * attention: 32-token block-local softmax attention with the chunk-INDEX scatter of lunar_evaluator.py:203-216,
+  * gradients: the set the reentrant checkpoints leave alive (shortcut.*, layer_scale, attention.proj.*, conv2.* of
+    blocks 1,2, gate.*, quality_heads.*) - everything else keeps grad None,
+  * BatchNorm running statistics: one update per forward plus one per checkpoint recompute.
+
+There is no CPU path: calling forward on a CPU tensor raises.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _capi, ops
+from ._capi import check
+
+_HEADS = 8
+_CHUNK = 32
+_SLOPE = 0.2
+
+
+def mish(x):
+    """x * tanh(softplus(x)) (reference lunar_evaluator.py:48-50)."""
+    return x * torch.tanh(F.softplus(x))
+
+
+# ====================================================================================================== module tree
+def _conv_act_bn(cin, cout, k, pad, groups=1):
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=k, padding=pad, groups=groups), nn.LeakyReLU(_SLOPE),
+                         nn.BatchNorm2d(cout))
+
+
+class PixelArtFeatureExtractor(nn.Module):
+    """Parameter container mirroring lunar_evaluator.py:57-112 (conv1, three depthwise+pointwise branches, fusion)."""
+
+    def __init__(self, in_channels=3, dropout_rate=0.1, feature_dim=128):
+        super().__init__()
+        self.conv1 = _conv_act_bn(in_channels, 32, 3, 1)
+
+        def branch(k):
+            return nn.Sequential(nn.Conv2d(32, 32, kernel_size=k, padding=k // 2, groups=32),
+                                 nn.Conv2d(32, 64, kernel_size=1), nn.LeakyReLU(_SLOPE), nn.BatchNorm2d(64))
+        self.edge_branch = branch(3)
+        self.color_branch = branch(5)
+        self.detail_branch = branch(3)
+        self.dropout = nn.Dropout(dropout_rate)
+        self.fusion = _conv_act_bn(64 * 3, feature_dim, 1, 0)
+
+    def forward(self, x):
+        feats, _ = _fe_forward(self, x, 1)
+        return _to_nchw(feats, x.shape[0], x.shape[2], x.shape[3])
+
+
+class PixelArtAttention(nn.Module):
+    """Parameter container mirroring lunar_evaluator.py:119-145; forward = as-executed block-local attention."""
+
+    def __init__(self, in_channels, num_heads=8, rel_pos_size=8, dropout=0.1, chunk_size=64):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = in_channels // num_heads
+        self.chunk_size = chunk_size
+        assert self.head_dim * num_heads == in_channels, "in_channels must be divisible by num_heads"
+        self.qkv = nn.Conv2d(in_channels, in_channels * 3, kernel_size=1)
+        self.proj = nn.Conv2d(in_channels, in_channels, kernel_size=1)
+        self.rel_pos_h = nn.Parameter(torch.randn(1, num_heads, rel_pos_size, 1) * 0.02)
+        self.rel_pos_w = nn.Parameter(torch.randn(1, num_heads, 1, rel_pos_size) * 0.02)
+        self.attn_drop = nn.Dropout(dropout)
+        self.proj_drop = nn.Dropout(dropout)
+        self.register_buffer('rel_pos_cache', None)
+        self.register_buffer('last_spatial_shapes', torch.zeros(2))
+
+    def _touch_rel_pos(self, H, W, device):
+        """Keeps the two state_dict buffers the reference creates on first use (lunar_evaluator.py:174-186). The
+        bias itself is constant along the softmax axis and never changes an output, so no kernel consumes it."""
+        if self.rel_pos_cache is not None and self.rel_pos_cache.shape[2] == H * W:
+            return
+        with torch.no_grad():
+            rel_h = F.interpolate(self.rel_pos_h, size=(H, 1), mode='bilinear', align_corners=True)
+            rel_w = F.interpolate(self.rel_pos_w, size=(1, W), mode='bilinear', align_corners=True)
+            self.rel_pos_cache = (rel_h.expand(-1, -1, -1, W) + rel_w.expand(-1, -1, H, -1)).reshape(
+                1, self.num_heads, H * W).unsqueeze(-1)
+            self.last_spatial_shapes = torch.tensor([H, W], device=device)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        h2, _ = _attention_forward(self, _to_nhwc(x), B, H, W, self.training, save=False)
+        return _to_nchw(h2, B, H, W)
+
+
+class ExpertBlock(nn.Module):
+    """Parameter container mirroring lunar_evaluator.py:234-258."""
+
+    def __init__(self, in_channels, out_channels, dropout_rate=0.1, rel_pos_size=8, layer_scale_init=0.1):
+        super().__init__()
+        def conv_stack(cin):
+            return nn.Sequential(nn.Conv2d(cin, out_channels, kernel_size=3, padding=1), nn.LeakyReLU(_SLOPE),
+                                 nn.BatchNorm2d(out_channels), nn.Dropout2d(dropout_rate))
+        self.conv1 = conv_stack(in_channels)
+        self.attention = PixelArtAttention(out_channels, rel_pos_size=rel_pos_size, dropout=dropout_rate)
+        self.conv2 = conv_stack(out_channels)
+        if in_channels != out_channels:
+            self.shortcut = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=1),
+                                          nn.BatchNorm2d(out_channels))
+        else:
+            self.shortcut = nn.Identity()
+        self.layer_scale = nn.Parameter(torch.ones(1, out_channels, 1, 1) * layer_scale_init)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        out, _ = _block_forward(self, _to_nhwc(x), B, H, W, self.training, 1, save=False, pool=None)
+        return _to_nchw(out, B, H, W)
+
+
+class LunarMoETeacher(nn.Module):
+    """Mixture-of-experts quality teacher, drop-in for lunar_evaluator.py:278-462."""
+
+    def __init__(self, num_experts=4, feature_dim=128, dropout_rate=0.1, rel_pos_size=8, use_checkpointing=True,
+                 expert_layers=3, intermediate_dim=256, embedding_dim=64):
+        super().__init__()
+        self.num_experts = num_experts
+        self.feature_dim = feature_dim
+        self.dropout_rate = dropout_rate
+        self.rel_pos_size = rel_pos_size
+        self.use_checkpointing = use_checkpointing
+        self.expert_layers = expert_layers
+        self.intermediate_dim = intermediate_dim
+        self.embedding_dim = embedding_dim
+
+        self.feature_extractor = PixelArtFeatureExtractor(in_channels=3, dropout_rate=dropout_rate, feature_dim=128)
+
+        def expert():
+            dims = [128] + [feature_dim] * expert_layers
+            return nn.Sequential(*[ExpertBlock(dims[i], dims[i + 1], dropout_rate=dropout_rate,
+                                               rel_pos_size=rel_pos_size) for i in range(expert_layers)])
+        self.experts = nn.ModuleList([expert() for _ in range(num_experts)])
+        self.gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(128, intermediate_dim),
+                                  nn.LeakyReLU(_SLOPE), nn.Dropout(dropout_rate),
+                                  nn.Linear(intermediate_dim, num_experts), nn.Softmax(dim=1))
+
+        def head(hidden, out, sigmoid=False):
+            layers = [nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.LayerNorm(feature_dim), nn.Linear(feature_dim, hidden),
+                      nn.LeakyReLU(_SLOPE), nn.Dropout(dropout_rate), nn.Linear(hidden, out)]
+            return nn.Sequential(*(layers + ([nn.Sigmoid()] if sigmoid else [])))
+        self.quality_heads = nn.ModuleList([head(intermediate_dim // 4, 4) for _ in range(num_experts)])
+        self.semantic_head = head(intermediate_dim // 2, 1, sigmoid=True)
+        self.style_net = head(intermediate_dim // 2, embedding_dim)
+        self.prompt_net = head(intermediate_dim // 2, embedding_dim)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, (nn.Conv2d, nn.Linear)):
+            nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='leaky_relu')
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, (nn.BatchNorm2d, nn.LayerNorm)):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+    def forward(self, x, prompt_embedding=None):
+        if not x.is_cuda:
+            raise _capi.LunarisB200Error("lunaris_orion_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        B, _, H, W = x.shape
+        hw = float(H * W)
+        grad_on = torch.is_grad_enabled() and self.training
+        params = _trunk_grad_params(self) if grad_on else []
+        res = _TeacherTrunk.apply(self, x.detach(), grad_on, *params)
+        pooled_fe, pooled = res[0], res[1:1 + self.num_experts]
+        fmaps = res[1 + self.num_experts:]
+
+        with torch.autocast("cuda", enabled=False):
+            weights = self.gate[2:](pooled_fe / hw)                               # Linear..Softmax on pooled feats
+            means = [p / hw for p in pooled]
+            quals = [self.quality_heads[e][2:](means[e]) for e in range(self.num_experts)]
+            wq = (torch.stack(quals, 1) * weights.unsqueeze(-1)).sum(1)
+            comb = (torch.stack(means, 1) * weights.unsqueeze(-1)).sum(1)
+            style = self.style_net[2:](comb)
+            prompt = self.prompt_net[2:](comb)
+            sem = self.semantic_head[2:](means[0])
+            sem = sem * F.cosine_similarity(prompt, prompt.detach(), dim=1).unsqueeze(1)
+        return {
+            'quality_scores': torch.sigmoid(wq),
+            'expert_weights': weights,
+            'style_embedding': style,
+            'prompt_embedding': prompt,
+            'semantic_score': sem,
+            'feature_maps': None if self.training else [_to_nchw(f, B, H, W) for f in fmaps],
+        }
+
+
+# ====================================================================================================== plumbing
+def _to_nhwc(x):
+    return x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _to_nchw(y, B, H, W):
+    return y.view(B, H, W, -1).permute(0, 3, 1, 2).float()
+
+
+_pack_cache = {}
+
+
+def _packed(param, kind):
+    """bf16 kernel-layout shadow of an fp32 parameter, refreshed when the optimizer changes it in place."""
+    key = (id(param), kind)
+    ent = _pack_cache.get(key)
+    ver = param._version
+    if ent is not None and ent[0] == ver and ent[1].device == param.device and ent[2] is param:
+        return ent[1]
+    if kind == "fwd":
+        t = ops.pack_conv_weight(param)
+    elif kind == "dgrad":
+        t = ops.pack_conv_weight_dgrad(param)
+    elif kind == "f32":
+        t = param.detach().float().contiguous()
+    else:
+        raise KeyError(kind)
+    _pack_cache[key] = (ver, t, param)
+    return t
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cpu_seed():
+    return int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _bn_train(bn, stats, n, n_updates):
+    """Batch statistics -> (scale, shift, mean, rstd); running buffers updated n_updates times."""
+    C = bn.num_features
+    out = torch.empty(4, C, device=stats.device, dtype=torch.float32)
+    check(_capi.lib().lun_bn_finalize(stats.data_ptr(), float(n), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                      bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                      bn.num_batches_tracked.data_ptr(), n_updates, bn.momentum, bn.eps,
+                                      out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), C,
+                                      _stream()), "lun_bn_finalize")
+    return out[0], out[1], out[2], out[3]
+
+
+def _bn_eval(bn):
+    scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+    return scale.contiguous(), (bn.bias.detach() - bn.running_mean * scale).contiguous()
+
+
+def _affine(x, B, HW, C, scale, shift, mask2d=None, ls=None, identity=None, id_scale=None, id_shift=None, pool=None,
+            seed=0, drop_p=0.0):
+    y = torch.empty_like(x)
+    check(_capi.lib().lun_affine_fwd_bf16(x.data_ptr(), _p(scale), _p(shift), _p(mask2d), _p(ls), _p(identity),
+                                          _p(id_scale), _p(id_shift), y.data_ptr(), _p(pool), seed, float(drop_p), B,
+                                          HW, C, _SLOPE, _stream()), "lun_affine_fwd_bf16")
+    return y
+
+
+def _drop2d_mask(B, C, p, device):
+    """Dropout2d keep-mask [B,C]: 0 or bf16(1/(1-p)) (what the reference's bf16 feature_dropout multiplies by)."""
+    keep = torch.empty(B, C, device=device, dtype=torch.float32).bernoulli_(1.0 - p)
+    return keep * float(torch.tensor(1.0 / (1.0 - p)).to(torch.bfloat16))
+
+
+# ====================================================================================================== forward pieces
+def _fe_forward(fe, x, n_updates):
+    """PixelArtFeatureExtractor.forward (lunar_evaluator.py:105-112). x: NCHW fp32. Returns NHWC bf16 [B,HW,128]
+    features and their per-image channel sums [B,128]."""
+    lib = _capi.lib()
+    B, _, H, W = x.shape
+    HW, dev = H * W, x.device
+    training = fe.training
+    x = x.detach().float().contiguous()
+    p_drop = fe.dropout.p if training else 0.0
+
+    c1, bn1 = fe.conv1[0], fe.conv1[2]
+    y0 = torch.empty(B, HW, 32, device=dev, dtype=torch.bfloat16)
+    st = torch.zeros(64, device=dev)
+    check(lib.lun_fe_conv1(x.data_ptr(), _packed(c1.weight, "f32").data_ptr(), _packed(c1.bias, "f32").data_ptr(),
+                           y0.data_ptr(), st.data_ptr(), B, H, W, _SLOPE, _stream()), "lun_fe_conv1")
+    sc0, sh0 = _bn_train(bn1, st, B * HW, n_updates)[:2] if training else _bn_eval(bn1)
+
+    branches = (fe.edge_branch, fe.color_branch, fe.detail_branch)
+    keep = [[_packed(getattr(br[i], a), "f32") for br in branches] for i, a in
+            ((0, "weight"), (0, "bias"), (1, "weight"), (1, "bias"))]
+    arrs = [(_capi.ctypes.c_void_p * 3)(*[t.data_ptr() for t in ts]) for ts in keep]
+    cat = torch.empty(B, HW, 192, device=dev, dtype=torch.bfloat16)
+    check(lib.lun_fe_branches(y0.data_ptr(), sc0.data_ptr(), sh0.data_ptr(), arrs[0], arrs[1], arrs[2], arrs[3],
+                              cat.data_ptr(), B, H, W, _SLOPE, _stream()), "lun_fe_branches")
+    if training:
+        st = torch.zeros(2 * 192, device=dev)
+        check(lib.lun_channel_stats_bf16(cat.data_ptr(), B * HW, 192, st.data_ptr(), _stream()),
+              "lun_channel_stats_bf16")
+        sums, sqs = st[:192], st[192:]
+        aff = [_bn_train(br[3], torch.cat([sums[64 * i:64 * i + 64], sqs[64 * i:64 * i + 64]]).contiguous(), B * HW,
+                         n_updates)[:2] for i, br in enumerate(branches)]
+    else:
+        aff = [_bn_eval(br[3]) for br in branches]
+    scale = torch.cat([a[0] for a in aff]).contiguous()
+    shift = torch.cat([a[1] for a in aff]).contiguous()
+    cat_n = _affine(cat, B, HW, 192, scale, shift, seed=_cpu_seed() if p_drop > 0 else 0, drop_p=p_drop)
+
+    cf, bnf = fe.fusion[0], fe.fusion[2]
+    C = cf.out_channels
+    st = torch.zeros(2 * C, device=dev) if training else None
+    f_pre = ops.conv2d_fprop(cat_n.view(B, H, W, 192), _packed(cf.weight, "fwd"), 1, 1, 0,
+                             bias=_packed(cf.bias, "f32"), act_leaky=True, stats=st, slope=_SLOPE)
+    scf, shf = _bn_train(bnf, st, B * HW, n_updates)[:2] if training else _bn_eval(bnf)
+    pooled = torch.zeros(B, C, device=dev)
+    feats = _affine(f_pre.view(B, HW, C), B, HW, C, scf, shf, pool=pooled)
+    return feats, pooled
+
+
+def _attention_forward(att, x1, B, H, W, training, save):
+    """PixelArtAttention.forward as executed (lunar_evaluator.py:189-227): qkv 1x1 conv, block-local attention for the
+    N/32+31 rows that survive the chunk-index scatter, proj on those rows, bias elsewhere, proj_drop.
+    x1: NHWC bf16 [B,HW,C]. Returns conv2's input h2 [B,HW,C] and what proj's backward needs."""
+    lib = _capi.lib()
+    C = att.qkv.in_channels
+    HW = H * W
+    nq = HW // _CHUNK + _CHUNK - 1
+    nq_pad = (nq + 7) // 8 * 8
+    p_attn = att.attn_drop.p if training else 0.0
+    p_proj = att.proj_drop.p if training else 0.0
+    att._touch_rel_pos(H, W, x1.device)
+    qkv = ops.conv2d_fprop(x1.view(B, H, W, C), _packed(att.qkv.weight, "fwd"), 1, 1, 0,
+                           bias=_packed(att.qkv.bias, "f32"))
+    att_small = torch.zeros(B, nq_pad, C, device=x1.device, dtype=torch.bfloat16)
+    check(lib.lun_attn_ref_rows_bf16(qkv.data_ptr(), att_small.data_ptr(), B, HW, C, att.num_heads, nq_pad,
+                                     _cpu_seed() if p_attn > 0 else 0, float(p_attn), _stream()),
+          "lun_attn_ref_rows_bf16")
+    del qkv
+    wp = _packed(att.proj.weight, "fwd")
+    proj_small = ops.linear_fprop(att_small.view(B * nq_pad, C), wp.view(C, C), _packed(att.proj.bias, "f32"),
+                                  out_f32=False)
+    seed = _cpu_seed() if p_proj > 0 else 0
+    h2 = torch.empty(B, HW, C, device=x1.device, dtype=torch.bfloat16)
+    check(lib.lun_proj_expand_bf16(proj_small.data_ptr(), _packed(att.proj.bias, "f32").data_ptr(), h2.data_ptr(), B,
+                                   HW, C, nq, nq_pad, seed, float(p_proj), _stream()), "lun_proj_expand_bf16")
+    saved = dict(att_small=att_small, seed=seed, p_proj=p_proj, nq=nq, nq_pad=nq_pad) if save else None
+    return h2, saved
+
+
+def _block_forward(blk, x, B, H, W, training, n_updates, save, pool):
+    """ExpertBlock.forward (lunar_evaluator.py:260-275) on NHWC bf16 x [B,HW,Cin]. Returns (out [B,HW,C], saved)."""
+    HW = H * W
+    dev = x.device
+    c1, bn1, d1 = blk.conv1[0], blk.conv1[2], blk.conv1[3]
+    c2, bn2, d2 = blk.conv2[0], blk.conv2[2], blk.conv2[3]
+    C, Cin = c1.out_channels, c1.in_channels
+    p2d = d1.p if training else 0.0
+
+    st = torch.zeros(2 * C, device=dev) if training else None
+    y1 = ops.conv2d_fprop(x.view(B, H, W, Cin), _packed(c1.weight, "fwd"), 3, 1, 1, bias=_packed(c1.bias, "f32"),
+                          act_leaky=True, stats=st, slope=_SLOPE)
+    sc1, sh1 = _bn_train(bn1, st, B * HW, n_updates)[:2] if training else _bn_eval(bn1)
+    m1 = _drop2d_mask(B, C, p2d, dev) if p2d > 0 else None
+    x1 = _affine(y1.view(B, HW, C), B, HW, C, sc1, sh1, mask2d=m1)
+    del y1
+    h2, att_saved = _attention_forward(blk.attention, x1, B, H, W, training, save)
+    del x1
+
+    st = torch.zeros(2 * C, device=dev) if training else None
+    y2 = ops.conv2d_fprop(h2.view(B, H, W, C), _packed(c2.weight, "fwd"), 3, 1, 1, bias=_packed(c2.bias, "f32"),
+                          act_leaky=True, stats=st, slope=_SLOPE).view(B, HW, C)
+    if training:
+        sc2, sh2, mean2, rstd2 = _bn_train(bn2, st, B * HW, n_updates)
+    else:
+        (sc2, sh2), mean2, rstd2 = _bn_eval(bn2), None, None
+    m2 = _drop2d_mask(B, C, d2.p, dev) if training and d2.p > 0 else None
+
+    has_sc = not isinstance(blk.shortcut, nn.Identity)
+    if has_sc:
+        cs, bns = blk.shortcut[0], blk.shortcut[1]
+        st = torch.zeros(2 * C, device=dev) if training else None
+        identity = ops.conv2d_fprop(x.view(B, H, W, Cin), _packed(cs.weight, "fwd"), 1, 1, 0,
+                                    bias=_packed(cs.bias, "f32"), stats=st).view(B, HW, C)
+        if training:
+            isc, ish, imean, irstd = _bn_train(bns, st, B * HW, n_updates)
+        else:
+            (isc, ish), imean, irstd = _bn_eval(bns), None, None
+    else:
+        identity, isc, ish, imean, irstd = x, None, None, None, None
+    ls = blk.layer_scale.detach().reshape(-1).contiguous()
+    out = _affine(y2, B, HW, C, sc2, sh2, mask2d=m2, ls=ls, identity=identity, id_scale=isc, id_shift=ish, pool=pool)
+    saved = None
+    if save:
+        saved = dict(att=att_saved, h2=h2, a2=y2, out=out, mean2=mean2, rstd2=rstd2, m2=m2, has_sc=has_sc)
+        if has_sc:
+            saved.update(sc_pre=identity, imean=imean, irstd=irstd, x=x)
+    return out, saved
+
+
+# ====================================================================================================== autograd trunk
+def _trunk_grad_params(teacher):
+    """Parameters that receive gradients in the reference's executed graph, fixed order."""
+    ps = []
+    for expert in teacher.experts:
+        for b, blk in enumerate(expert):
+            if b == 0:
+                if not isinstance(blk.shortcut, nn.Identity):
+                    ps += [blk.shortcut[0].weight, blk.shortcut[0].bias, blk.shortcut[1].weight, blk.shortcut[1].bias]
+            else:
+                ps += [blk.layer_scale, blk.attention.proj.weight, blk.attention.proj.bias, blk.conv2[0].weight,
+                       blk.conv2[0].bias, blk.conv2[2].weight, blk.conv2[2].bias]
+    return ps
+
+
+def _block_tail_backward(B, HW, C, dout, gpool, out, bn_in, mean, rstd, gamma, ls, m2, slope_out, slope_a, want_dpre):
+    """Backward through leaky_relu(residual) -> layer_scale -> Dropout2d -> BatchNorm -> LeakyReLU.
+    Returns (dpre, dz, dbias_conv, t1, t2)."""
+    lib = _capi.lib()
+    dev = bn_in.device
+    t = torch.zeros(2, C, device=dev)
+    dpre = torch.empty(B, HW, C, device=dev, dtype=torch.bfloat16) if want_dpre else None
+    check(lib.lun_block_bwd_reduce_bf16(_p(dout), _p(gpool), _p(out), bn_in.data_ptr(), mean.data_ptr(),
+                                        rstd.data_ptr(), _p(m2), _p(dpre), t[0].data_ptr(), t[1].data_ptr(), B, HW, C,
+                                        slope_out, _stream()), "lun_block_bwd_reduce_bf16")
+    dz = torch.empty(B, HW, C, device=dev, dtype=torch.bfloat16)
+    dbias = torch.zeros(C, device=dev)
+    check(lib.lun_block_bwd_apply_bf16(_p(dpre), None if dpre is not None else _p(gpool),
+                                       None if dpre is not None else _p(out), bn_in.data_ptr(), mean.data_ptr(),
+                                       rstd.data_ptr(), gamma.data_ptr(), _p(ls), _p(m2), t[0].data_ptr(),
+                                       t[1].data_ptr(), dz.data_ptr(), dbias.data_ptr(), B, HW, C, slope_out, slope_a,
+                                       _stream()), "lun_block_bwd_apply_bf16")
+    return dpre, dz, dbias, t[0], t[1]
+
+
+class _TeacherTrunk(torch.autograd.Function):
+    """images -> (sum-pooled FE features, sum-pooled expert outputs[, feature maps in eval]) with the reference's
+    executed gradient set as backward."""
+
+    @staticmethod
+    def forward(ctx, teacher, x, grad_on, *params):
+        B, _, H, W = x.shape
+        training = teacher.training
+        feats, pooled_fe = _fe_forward(teacher.feature_extractor, x, 1)
+        pooled, fmaps, saved = [], [], []
+        for expert in teacher.experts:
+            h = feats
+            per = []
+            C = expert[0].conv1[0].out_channels
+            for b, blk in enumerate(expert):
+                last = b == len(expert) - 1
+                pool = torch.zeros(B, C, device=x.device) if last else None
+                # blocks whose checkpoint segment the reference re-runs in backward update BN stats twice
+                recomputed = grad_on and b > 0
+                h, sv = _block_forward(blk, h, B, H, W, training, 2 if recomputed else 1, save=grad_on, pool=pool)
+                per.append(sv)
+                if last:
+                    pooled.append(pool)
+            saved.append(per)
+            if not training:
+                fmaps.append(h)
+        ctx.teacher, ctx.saved, ctx.grad_on = teacher, saved, grad_on
+        ctx.dims = (B, H, W)
+        ctx.feats = feats if grad_on else None
+        outs = (pooled_fe, *pooled, *fmaps)
+        ctx.mark_non_differentiable(pooled_fe, *fmaps)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_fe, *gs):
+        teacher = ctx.teacher
+        B, H, W = ctx.dims
+        HW = H * W
+        grads = []
+        for e, expert in enumerate(teacher.experts):
+            C = expert[0].conv1[0].out_channels
+            gp = gs[e]
+            per_block = {}
+            dout = None
+            gpool = gp.contiguous().float() if gp is not None else torch.zeros(B, C, device=ctx.feats.device)
+            for b in range(len(expert) - 1, 0, -1):
+                blk, sv = expert[b], ctx.saved[e][b]
+                gamma, beta = blk.conv2[2].weight.detach(), blk.conv2[2].bias.detach()
+                ls = blk.layer_scale.detach().reshape(-1).contiguous()
+                dpre, dz, dbias2, t1, t2 = _block_tail_backward(
+                    B, HW, C, dout, gpool if dout is None else None, sv["out"], sv["a2"], sv["mean2"], sv["rstd2"],
+                    gamma, ls, sv["m2"], _SLOPE, _SLOPE, want_dpre=True)
+                d_ls = (gamma * t2 + beta * t1).view(1, C, 1, 1)
+                d_gamma, d_beta = ls * t2, ls * t1
+                dz4 = dz.view(B, H, W, C)
+                dw2 = ops.conv2d_wgrad(dz4, sv["h2"].view(B, H, W, C), 3, 1, 1)
+                dh2 = ops.conv2d_dgrad(dz4, _packed(blk.conv2[0].weight, "dgrad"), 3, 1, 1, (H, W))
+                del dz, dz4
+                a = sv["att"]
+                dpo = torch.zeros(B, a["nq_pad"], C, device=dh2.device, dtype=torch.bfloat16)
+                dbp = torch.zeros(C, device=dh2.device)
+                check(_capi.lib().lun_proj_bwd_gather_bf16(dh2.data_ptr(), dpo.data_ptr(), dbp.data_ptr(), B, HW, C,
+                                                           a["nq"], a["nq_pad"], a["seed"], float(a["p_proj"]),
+                                                           _stream()), "lun_proj_bwd_gather_bf16")
+                del dh2
+                dwp = ops.linear_wgrad(dpo.view(B * a["nq_pad"], C), a["att_small"].view(B * a["nq_pad"], C))
+                per_block[b] = [d_ls, dwp.view(C, C, 1, 1), dbp, dw2, dbias2, d_gamma, d_beta]
+                dout = dpre
+            blk, sv = expert[0], ctx.saved[e][0]
+            if sv["has_sc"]:
+                bns = blk.shortcut[1]
+                _, dzs, dbs, t1, t2 = _block_tail_backward(
+                    B, HW, C, dout, gpool if dout is None else None, sv["out"], sv["sc_pre"], sv["imean"],
+                    sv["irstd"], bns.weight.detach(), None, None, _SLOPE, 1.0, want_dpre=True)
+                cin = blk.shortcut[0].in_channels
+                dws = ops.conv2d_wgrad(dzs.view(B, H, W, C), sv["x"].view(B, H, W, cin), 1, 1, 0)
+                grads += [dws, dbs, t2.clone(), t1.clone()]
+            for b in range(1, len(expert)):
+                grads += per_block[b]
+        ctx.saved = None
+        ctx.feats = None
+        return (None, None, None, *grads)
