@@ -118,6 +118,43 @@ int lun_fe_branches(const void* y0, const float* scale, const float* shift, cons
                     const float* const* dw_b, const float* const* pw_w, const float* const* pw_b, void* cat, int B,
                     int H, int W, float slope, void* stream);
 
+/* ---- VAE kernels (LunarisCoreVAE, lunar_generate.py) --------------------------------------------------------- */
+
+/* Per-image channel sums: stats[b][0][c] = sum_hw x, stats[b][1][c] = sum_hw x^2 (caller zeroes). Feeds GroupNorm. */
+int lun_image_channel_stats_bf16(const void* x, float* stats, int B, int HW, int C, void* stream);
+
+/* y = mish(group_norm(x));  if res: y = mish(y + res) (ResBlock tail, lunar_generate.py:53);  if add: y += add
+ * (decoder skip connection, :212-222). Reference: nn.GroupNorm(8,C) + nn.Mish, lunar_generate.py:37-38,96-97,170-171. */
+int lun_gn_mish_fwd_bf16(const void* x, const float* stats, const float* gamma, const float* beta, const void* res,
+                         const void* add, void* y, int B, int HW, int C, int groups, float eps, void* stream);
+
+/* Backward of the above (two launches: reduce + apply). dy2 (nullable) is added to dy (two consumers of the same
+ * activation). red[b][0][c] = sum_hw dyh, red[b][1][c] = sum_hw dyh*xhat (caller zeroes) give dbeta / dgamma after a
+ * sum over b. dx = gradient at the conv output; dres (when res != null) = gradient of the residual input. */
+int lun_gn_mish_bwd_bf16(const void* dy, const void* dy2, const void* x, const float* stats, const float* gamma,
+                         const float* beta, const void* res, float* red, void* dx, void* dres, int B, int HW, int C,
+                         int groups, float eps, void* stream);
+
+/* Encoder first layer: conv3x3 (3 -> cout=64, stride 1|2, pad 1) on NCHW fp32 images -> NHWC bf16
+ * (lunar_generate.py:95), and its weight / bias gradient (dw [cout,3,3,3], db [cout], caller zeroes). */
+int lun_conv3x3_c3_fwd(const float* x_nchw, const float* w, const float* bias, void* y, int B, int H, int W, int cout,
+                       int stride, void* stream);
+int lun_conv3x3_c3_wgrad(const void* dy, const float* x_nchw, float* dw, float* db, int B, int H, int W, int cout,
+                         int stride, void* stream);
+
+/* Decoder last layer: recon = tanh(conv3x3(x, 32 -> 3) + bias) as NCHW fp32 (lunar_generate.py:226-228) and its
+ * backward: dx (NHWC bf16), dw [3,32,3,3], db [3] (caller zeroes dw, db). */
+int lun_final_conv_tanh_fwd(const void* x, const float* w, const float* bias, float* recon, int B, int H, int W,
+                            void* stream);
+int lun_final_conv_bwd(const float* drecon, const float* recon, const void* x, const float* w, void* dx, float* dw,
+                       float* db, int B, int H, int W, void* stream);
+
+/* z = mu + eps*exp(logvar/2) with mu|logvar packed as mulv[B,2L] (lunar_generate.py:259-261), and the backward that
+ * merges dz with the direct gradients of mu / logvar (KL term) into dmulv[B,2L] bf16. */
+int lun_reparam_fwd(const float* mulv, const float* eps, void* z, int B, int L, void* stream);
+int lun_reparam_bwd(const float* mulv, const float* eps, const void* dz, const float* dmu, const float* dlogvar,
+                    void* dmulv, int B, int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,18 @@ SIGNATURES = {
     "lun_proj_bwd_gather_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_float,
                                  c_void_p],
     "lun_fe_conv1": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],
+    "lun_image_channel_stats_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "lun_gn_mish_fwd_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                             c_int, c_float, c_void_p],
+    "lun_gn_mish_bwd_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "lun_conv3x3_c3_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "lun_conv3x3_c3_wgrad": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "lun_final_conv_tanh_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "lun_final_conv_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                           c_void_p],
+    "lun_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "lun_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "lun_fe_branches": [c_void_p, c_void_p, c_void_p, c_pp, c_pp, c_pp, c_pp, c_void_p, c_int, c_int, c_int, c_float,
                         c_void_p],
 }

@@ -51,7 +51,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_blocks = g.Cout / block_n;
   const int m_tiles = g.ntb * g.nth * g.ntw;
   const int total_tiles = m_tiles * n_blocks;
-  const int kchunks = g.Cin >> 6;
+  const int kchunks = (g.Cin + 63) >> 6;   // a ragged last chunk is zero-filled by TMA (both operands)
   const int ksteps = g.ntaps * kchunks;
   const uint32_t tmem_cols = (2 * block_n <= 32) ? 32u : (2 * block_n <= 64) ? 64u : (2 * block_n <= 128) ? 128u
                              : (2 * block_n <= 256) ? 256u : 512u;
@@ -358,7 +358,7 @@ bool tile_grid(int GB, int GH, int GW, int pixels, int* TB, int* TH, int* TW) {
 // x: NHWC bf16 [XB, XH, XW, Cin]; wpk: [nslabs][Cout][Cin] bf16; out: [*, OH, OW, ldo]
 int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, int nslabs, ConvGeom g,
                       const float* bias, void* out, float* stats, cudaStream_t stream) {
-  if (g.Cin % 64 != 0 || g.block_n % 32 != 0 || g.block_n > 256 || g.Cout % g.block_n != 0) return 2;
+  if (g.Cin % 8 != 0 || g.block_n % 32 != 0 || g.block_n > 256 || g.Cout % g.block_n != 0) return 2;
   if (g.ntaps < 1 || g.ntaps > kMaxTaps) return 3;
   if (!tile_grid(g.GB, g.GH, g.GW, 128, &g.TB, &g.TH, &g.TW)) return 4;
   g.ntw = g.GW / g.TW;

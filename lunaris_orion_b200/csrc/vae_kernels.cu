@@ -1,0 +1,567 @@
+// CUDA-core kernels of the VAE path (LunarisCoreVAE, lunar_generate.py): GroupNorm(8)+Mish forward / backward with the
+// ResBlock and skip-connection adds fused, the 3-channel first / last convolutions (too thin for the tensor cores),
+// and the reparameterisation. Activations are NHWC bf16 [B, HW, C]; images are NCHW fp32 as the trainer hands them.
+#include "../../include/lunaris_b200.h"
+#include "elem_common.cuh"
+
+namespace lun {
+
+constexpr int kVT = 256;
+
+__device__ __forceinline__ float softplus_f(float v) { return v > 20.f ? v : log1pf(__expf(v)); }
+__device__ __forceinline__ float mish_f(float v) { return v * tanhf(softplus_f(v)); }
+__device__ __forceinline__ float mish_grad_f(float v) {
+  const float t = tanhf(softplus_f(v));
+  const float sg = 1.f / (1.f + __expf(-v));
+  return t + v * (1.f - t * t) * sg;
+}
+
+// ------------------------------------------------------------------------------------------- per-image channel sums
+// stats[b][0][c] = sum_hw x, stats[b][1][c] = sum_hw x^2   (caller zeroes)
+__global__ void __launch_bounds__(kVT) image_channel_stats_kernel(const bf16* __restrict__ x,
+                                                                  float* __restrict__ stats, int HW, int C) {
+  extern __shared__ float smem[];
+  const int cg = C >> 3, lanes = kVT / cg;
+  const int cgi = threadIdx.x % cg, lane_px = threadIdx.x / cg;
+  const bool active = lane_px < lanes;
+  const int b = blockIdx.y;
+  float a1[8] = {}, a2[8] = {};
+  if (active) {
+    for (int p = blockIdx.x * lanes + lane_px; p < HW; p += gridDim.x * lanes) {
+      float v[8];
+      load8(x + ((size_t)b * HW + p) * C + cgi * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += v[j];
+        a2[j] += v[j] * v[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      smem[(lane_px * 2 + 0) * C + cgi * 8 + j] = a1[j];
+      smem[(lane_px * 2 + 1) * C + cgi * 8 + j] = a2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kVT) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += smem[l * 2 * C + i];
+    atomicAdd(stats + (size_t)b * 2 * C + i, s);
+  }
+}
+
+// group mean / rstd of channel c's group from the per-image channel sums
+__device__ __forceinline__ void group_stats(const float* __restrict__ st, int C, int cpg, int c, float inv_m, float eps,
+                                            float* mean, float* rstd) {
+  const int g0 = (c / cpg) * cpg;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < cpg; ++k) {
+    s1 += st[g0 + k];
+    s2 += st[C + g0 + k];
+  }
+  const float m = s1 * inv_m;
+  float var = s2 * inv_m - m * m;
+  var = var < 0.f ? 0.f : var;
+  *mean = m;
+  *rstd = rsqrtf(var + eps);
+}
+
+// ------------------------------------------------------------------------------------------- GroupNorm + Mish forward
+// y = mish(gn(x));  if (res) y = mish(y + res);  if (add) y = y + add      (lunar_generate.py:37-38,53,96-97,212-222)
+__global__ void __launch_bounds__(kVT) gn_mish_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const bf16* __restrict__ res,
+                                                          const bf16* __restrict__ add, bf16* __restrict__ y, int HW,
+                                                          int C, int groups, float eps) {
+  const int cg = C >> 3, lanes = kVT / cg;
+  const int cgi = threadIdx.x % cg, lane_px = threadIdx.x / cg;
+  if (lane_px >= lanes) return;
+  const int b = blockIdx.y, c0 = cgi * 8, cpg = C / groups;
+  const float inv_m = 1.f / ((float)cpg * (float)HW);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float mean, rstd;
+    group_stats(stats + (size_t)b * 2 * C, C, cpg, c0 + j, inv_m, eps, &mean, &rstd);
+    sc[j] = gamma[c0 + j] * rstd;
+    sh[j] = beta[c0 + j] - mean * sc[j];
+  }
+  for (int p = blockIdx.x * lanes + lane_px; p < HW; p += gridDim.x * lanes) {
+    const size_t off = ((size_t)b * HW + p) * C + c0;
+    float v[8];
+    load8(x + off, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = mish_f(v[j] * sc[j] + sh[j]);
+    if (res) {
+      float r[8];
+      load8(res + off, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = mish_f(v[j] + r[j]);
+    }
+    if (add) {
+      float r[8];
+      load8(add + off, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    store8(y + off, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- GroupNorm + Mish backward
+// Recomputes the forward from x; dyh = gradient at the GroupNorm output. pass 0 (reduce): red[b][0][c] = sum dyh,
+// red[b][1][c] = sum dyh*xhat. pass 1 (apply): dx = rstd*(gamma*dyh - S1/m - xhat*S2/m) with group sums S1,S2 of
+// gamma-weighted red; when res != null also writes dres = dy * mish'(mish(gn)+res).
+template <int PASS>
+__global__ void __launch_bounds__(kVT) gn_mish_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2,
+                                                          const bf16* __restrict__ x,
+                                                          const float* __restrict__ stats,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const bf16* __restrict__ res,
+                                                          float* __restrict__ red, bf16* __restrict__ dx,
+                                                          bf16* __restrict__ dres, int HW, int C, int groups,
+                                                          float eps) {
+  extern __shared__ float smem[];
+  const int cg = C >> 3, lanes = kVT / cg;
+  const int cgi = threadIdx.x % cg, lane_px = threadIdx.x / cg;
+  const bool active = lane_px < lanes;
+  const int b = blockIdx.y, c0 = cgi * 8, cpg = C / groups;
+  const float inv_m = 1.f / ((float)cpg * (float)HW);
+  float mean[8], rstd[8], gm[8], bt[8], s1[8], s2[8], a1[8] = {}, a2[8] = {};
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      group_stats(stats + (size_t)b * 2 * C, C, cpg, c, inv_m, eps, &mean[j], &rstd[j]);
+      gm[j] = gamma[c];
+      bt[j] = beta[c];
+      if (PASS == 1) {
+        const int g0 = (c / cpg) * cpg;
+        float t1 = 0.f, t2 = 0.f;
+        for (int k = 0; k < cpg; ++k) {
+          t1 += gamma[g0 + k] * red[(size_t)b * 2 * C + g0 + k];
+          t2 += gamma[g0 + k] * red[(size_t)b * 2 * C + C + g0 + k];
+        }
+        s1[j] = t1 * inv_m;
+        s2[j] = t2 * inv_m;
+      }
+    }
+    for (int p = blockIdx.x * lanes + lane_px; p < HW; p += gridDim.x * lanes) {
+      const size_t off = ((size_t)b * HW + p) * C + c0;
+      float d[8], xv[8], r[8], dr[8];
+      load8(dy + off, d);
+      if (dy2) {
+        float d2[8];
+        load8(dy2 + off, d2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += d2[j];
+      }
+      load8(x + off, xv);
+      if (res) load8(res + off, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mean[j]) * rstd[j];
+        const float u = xh * gm[j] + bt[j];
+        float g = d[j];
+        if (res) {
+          g *= mish_grad_f(mish_f(u) + r[j]);
+          dr[j] = g;
+        }
+        g *= mish_grad_f(u);
+        if (PASS == 0) {
+          a1[j] += g;
+          a2[j] += g * xh;
+        } else {
+          d[j] = rstd[j] * (gm[j] * g - s1[j] - xh * s2[j]);
+        }
+      }
+      if (PASS == 1) {
+        store8(dx + off, d);
+        if (res && dres) store8(dres + off, dr);
+      }
+    }
+  }
+  if (PASS == 0) {
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        smem[(lane_px * 2 + 0) * C + c0 + j] = a1[j];
+        smem[(lane_px * 2 + 1) * C + c0 + j] = a2[j];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kVT) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += smem[l * 2 * C + i];
+      atomicAdd(red + (size_t)b * 2 * C + i, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- 3-channel input conv
+// y[b,oh,ow,:] = act(conv3x3(x_nchw[b,0:3], w) + bias), stride 1 or 2, pad 1; NHWC bf16 output with COUT channels.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, bf16* __restrict__ y,
+                                                             int B, int H, int W, int stride) {
+  __shared__ float sw[27][COUT];
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += 256) sw[i / COUT][i % COUT] = rbf(w[(i % COUT) * 27 + i / COUT]);
+  for (int i = threadIdx.x; i < COUT; i += 256) sb[i] = bias[i];
+  __syncthreads();
+  const int OH = H / stride, OW = W / stride;
+  const long total = (long)B * OH * OW;
+  const long p = (long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= total) return;
+  const int b = (int)(p / ((long)OH * OW)), r = (int)(p % ((long)OH * OW)), oh = r / OW, ow = r % OW;
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    const float* xc = x + ((long)b * 3 + c) * H * W;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * stride + kh - 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * stride + kw - 1;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = rbf(__ldg(xc + (long)ih * W + iw));
+        const float* wr = sw[(c * 3 + kh) * 3 + kw];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] += v * wr[o];
+      }
+    }
+  }
+  bf16* dst = y + p * COUT;
+#pragma unroll
+  for (int j = 0; j < COUT / 8; ++j) {
+    float v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = acc[8 * j + i] + sb[8 * j + i];
+    store8(dst + 8 * j, v8);
+  }
+}
+
+// dW[o][c][kh][kw] += sum_pixels dy[b,oh,ow,o] * x[b,c,ih,iw];  db[o] += sum dy.  256 pixels per block iteration.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_c3_wgrad_kernel(const bf16* __restrict__ dy,
+                                                               const float* __restrict__ x, float* __restrict__ dw,
+                                                               float* __restrict__ db, int B, int H, int W,
+                                                               int stride) {
+  __shared__ float s_dy[64][COUT + 1];
+  __shared__ float s_x[64][28];
+  const int OH = H / stride, OW = W / stride;
+  const long total = (long)B * OH * OW;
+  // thread -> (o, tap group): 256 threads = COUT x (256/COUT) groups; 28 slots (27 taps + 1 for the bias) split up
+  const int o = threadIdx.x % COUT, grp = threadIdx.x / COUT, ngrp = 256 / COUT;
+  const int k_per = (28 + ngrp - 1) / ngrp;
+  float acc[28];
+#pragma unroll
+  for (int k = 0; k < 28; ++k) acc[k] = 0.f;
+  for (long base = (long)blockIdx.x * 64; base < total; base += (long)gridDim.x * 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * COUT; i += 256) {
+      const long p = base + i / COUT;
+      s_dy[i / COUT][i % COUT] = p < total ? __bfloat162float(dy[p * COUT + i % COUT]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64 * 28; i += 256) {
+      const int pi = i / 28, k = i % 28;
+      const long p = base + pi;
+      float v = 0.f;
+      if (p < total) {
+        if (k == 27) v = 1.f;
+        else {
+          const int b = (int)(p / ((long)OH * OW)), r = (int)(p % ((long)OH * OW)), oh = r / OW, ow = r % OW;
+          const int c = k / 9, kh = (k / 3) % 3, kw = k % 3;
+          const int ih = oh * stride + kh - 1, iw = ow * stride + kw - 1;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = rbf(x[(((long)b * 3 + c) * H + ih) * W + iw]);
+        }
+      }
+      s_x[pi][k] = v;
+    }
+    __syncthreads();
+    for (int pi = 0; pi < 64; ++pi) {
+      const float d = s_dy[pi][o];
+#pragma unroll
+      for (int kk = 0; kk < 28; ++kk) {
+        if (kk < k_per) {
+          const int k = grp * k_per + kk;
+          if (k < 28) acc[kk] += d * s_x[pi][k];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int kk = 0; kk < 28; ++kk) {
+    if (kk < k_per) {
+      const int k = grp * k_per + kk;
+      if (k < 27) atomicAdd(dw + o * 27 + k, acc[kk]);
+      else if (k == 27) atomicAdd(db + o, acc[kk]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- final conv 32->3 + tanh
+// recon[b,o,h,w] = tanh(conv3x3(x_nhwc[b], w[o]) + bias[o]), NCHW fp32 output (lunar_generate.py:226-228).
+__global__ void __launch_bounds__(256) final_conv_tanh_fwd_kernel(const bf16* __restrict__ x,
+                                                                  const float* __restrict__ w,
+                                                                  const float* __restrict__ bias,
+                                                                  float* __restrict__ recon, int B, int H, int W) {
+  __shared__ float sw[9][3][32];
+  for (int i = threadIdx.x; i < 864; i += 256) {
+    const int o = i / 288, ci = (i / 9) % 32, t = i % 9;    // reference layout [o][ci][kh][kw]
+    sw[t][o][ci] = rbf(w[i]);
+  }
+  __syncthreads();
+  const long total = (long)B * H * W;
+  const long p = (long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= total) return;
+  const int b = (int)(p / ((long)H * W)), r = (int)(p % ((long)H * W)), h = r / W, wq = r % W;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = h + kh - 1;
+    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = wq + kw - 1;
+      if (iw < 0 || iw >= W) continue;
+      const bf16* xp = x + (((long)b * H + ih) * W + iw) * 32;
+      const int t = kh * 3 + kw;
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float v[8];
+        load8(xp + c8 * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a0 += v[j] * sw[t][0][c8 * 8 + j];
+          a1 += v[j] * sw[t][1][c8 * 8 + j];
+          a2 += v[j] * sw[t][2][c8 * 8 + j];
+        }
+      }
+    }
+  }
+  const long hw = (long)H * W;
+  float* dst = recon + (long)b * 3 * hw + r;
+  dst[0] = tanhf(rbf(a0 + bias[0]));
+  dst[hw] = tanhf(rbf(a1 + bias[1]));
+  dst[2 * hw] = tanhf(rbf(a2 + bias[2]));
+}
+
+// dx[b,h,w,ci] = sum_{o,taps} dpre[b,o,h+1-kh,w+1-kw] * w[o][ci][kh][kw],  dpre = drecon * (1 - recon^2)
+__global__ void __launch_bounds__(256) final_conv_dgrad_kernel(const float* __restrict__ drecon,
+                                                               const float* __restrict__ recon,
+                                                               const float* __restrict__ w, bf16* __restrict__ dx,
+                                                               int B, int H, int W) {
+  __shared__ float sw[9][3][32];
+  for (int i = threadIdx.x; i < 864; i += 256) {
+    const int o = i / 288, ci = (i / 9) % 32, t = i % 9;
+    sw[t][o][ci] = rbf(w[i]);
+  }
+  __syncthreads();
+  const long total = (long)B * H * W, hw = (long)H * W;
+  const long p = (long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= total) return;
+  const int b = (int)(p / hw), r = (int)(p % hw), h = r / W, wq = r % W;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int oh = h + 1 - kh;
+    if (oh < 0 || oh >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ow = wq + 1 - kw;
+      if (ow < 0 || ow >= W) continue;
+      const long q = (long)b * 3 * hw + (long)oh * W + ow;
+      float d[3];
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const float rc = recon[q + o * hw];
+        d[o] = rbf(drecon[q + o * hw] * (1.f - rc * rc));
+      }
+      const int t = kh * 3 + kw;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] += d[0] * sw[t][0][c] + d[1] * sw[t][1][c] + d[2] * sw[t][2][c];
+    }
+  }
+  bf16* dst = dx + p * 32;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = acc[8 * j + i];
+    store8(dst + 8 * j, v8);
+  }
+}
+
+// dW[o][ci][kh][kw] += sum_pixels dpre[b,o,h,w] * x[b,h+kh-1,w+kw-1,ci];  db[o] += sum dpre.
+// One block per 16x16 pixel tile; thread (tap, ci) for 288 threads, 3 more for the bias.
+__global__ void __launch_bounds__(320) final_conv_wgrad_kernel(const float* __restrict__ drecon,
+                                                               const float* __restrict__ recon,
+                                                               const bf16* __restrict__ x, float* __restrict__ dw,
+                                                               float* __restrict__ db, int H, int W) {
+  __shared__ float s_x[18 * 18][33];
+  __shared__ float s_d[256][3];
+  const int b = blockIdx.z, h0 = blockIdx.y * 16, w0 = blockIdx.x * 16;
+  const long hw = (long)H * W;
+  for (int i = threadIdx.x; i < 18 * 18 * 4; i += 320) {
+    const int c8 = i & 3, px = i >> 2, ty = px / 18, tx = px % 18;
+    const int ih = h0 + ty - 1, iw = w0 + tx - 1;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) load8(x + (((long)b * H + ih) * W + iw) * 32 + c8 * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_x[px][c8 * 8 + j] = v[j];
+  }
+  for (int i = threadIdx.x; i < 768; i += 320) {
+    const int o = i / 256, px = i % 256;
+    const long q = ((long)b * 3 + o) * hw + (long)(h0 + px / 16) * W + w0 + px % 16;
+    const float rc = recon[q];
+    s_d[px][o] = rbf(drecon[q] * (1.f - rc * rc));
+  }
+  __syncthreads();
+  if (threadIdx.x < 288) {
+    const int ci = threadIdx.x % 32, t = threadIdx.x / 32, kh = t / 3, kw = t % 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int px = 0; px < 256; ++px) {
+      const float xv = s_x[(px / 16 + kh) * 18 + px % 16 + kw][ci];
+      a0 += s_d[px][0] * xv;
+      a1 += s_d[px][1] * xv;
+      a2 += s_d[px][2] * xv;
+    }
+    atomicAdd(dw + (0 * 32 + ci) * 9 + t, a0);
+    atomicAdd(dw + (1 * 32 + ci) * 9 + t, a1);
+    atomicAdd(dw + (2 * 32 + ci) * 9 + t, a2);
+  } else if (threadIdx.x < 291) {
+    const int o = threadIdx.x - 288;
+    float a = 0.f;
+    for (int px = 0; px < 256; ++px) a += s_d[px][o];
+    atomicAdd(db + o, a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- reparameterisation
+// z = mu + eps * exp(0.5*logvar)  (lunar_generate.py:259-261); mu/logvar come packed as mulv[B, 2L] (fused fc).
+__global__ void reparam_fwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
+                                   bf16* __restrict__ z, int B, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L) return;
+  const int b = i / L, l = i % L;
+  const float mu = mulv[(size_t)b * 2 * L + l], lv = mulv[(size_t)b * 2 * L + L + l];
+  z[i] = __float2bfloat16_rn(mu + eps[i] * __expf(0.5f * lv));
+}
+// d(mulv) = [dmu + dz | dlogvar + dz * eps * 0.5 * exp(0.5*logvar)] as bf16 for the fused fc backward
+__global__ void reparam_bwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
+                                   const bf16* __restrict__ dz, const float* __restrict__ dmu,
+                                   const float* __restrict__ dlv, bf16* __restrict__ dmulv, int B, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L) return;
+  const int b = i / L, l = i % L;
+  const float lv = mulv[(size_t)b * 2 * L + L + l];
+  const float g = __bfloat162float(dz[i]);
+  const float gm = (dmu ? dmu[i] : 0.f) + g;
+  const float gl = (dlv ? dlv[i] : 0.f) + g * eps[i] * 0.5f * __expf(0.5f * lv);
+  dmulv[(size_t)b * 2 * L + l] = __float2bfloat16_rn(gm);
+  dmulv[(size_t)b * 2 * L + L + l] = __float2bfloat16_rn(gl);
+}
+
+static int vae_blocks(int HW, int C, int B) {
+  const int lanes = kVT / (C / 8);
+  int per = (HW + lanes - 1) / lanes;
+  int want = (148 * 4 + B - 1) / B;
+  if (want < 1) want = 1;
+  return per < want ? per : want;
+}
+
+}  // namespace lun
+
+using namespace lun;
+
+#define LUN_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH)
+
+extern "C" {
+
+int lun_image_channel_stats_bf16(const void* x, float* stats, int B, int HW, int C, void* stream) {
+  if (C % 8 || C / 8 > kVT) return LUN_E_SHAPE;
+  const int lanes = kVT / (C / 8);
+  dim3 grid(vae_blocks(HW, C, B), B);
+  image_channel_stats_kernel<<<grid, kVT, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x,
+                                                                                                 stats, HW, C);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_gn_mish_fwd_bf16(const void* x, const float* stats, const float* gamma, const float* beta, const void* res,
+                         const void* add, void* y, int B, int HW, int C, int groups, float eps, void* stream) {
+  if (C % 8 || C / 8 > kVT || C % groups) return LUN_E_SHAPE;
+  dim3 grid(vae_blocks(HW, C, B), B);
+  gn_mish_fwd_kernel<<<grid, kVT, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, gamma, beta, (const bf16*)res,
+                                                             (const bf16*)add, (bf16*)y, HW, C, groups, eps);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_gn_mish_bwd_bf16(const void* dy, const void* dy2, const void* x, const float* stats, const float* gamma, const float* beta,
+                         const void* res, float* red, void* dx, void* dres, int B, int HW, int C, int groups,
+                         float eps, void* stream) {
+  if (C % 8 || C / 8 > kVT || C % groups) return LUN_E_SHAPE;
+  const int lanes = kVT / (C / 8);
+  dim3 grid(vae_blocks(HW, C, B), B);
+  gn_mish_bwd_kernel<0><<<grid, kVT, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)dy2, (const bf16*)x, stats, gamma, beta, (const bf16*)res, red, nullptr, nullptr,
+      HW, C, groups, eps);
+  gn_mish_bwd_kernel<1><<<grid, kVT, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)x,
+                                                                stats, gamma, beta, (const bf16*)res, red, (bf16*)dx,
+                                                                (bf16*)dres, HW, C, groups, eps);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_conv3x3_c3_fwd(const float* x_nchw, const float* w, const float* bias, void* y, int B, int H, int W, int cout,
+                       int stride, void* stream) {
+  if (cout != 64 || (stride != 1 && stride != 2)) return LUN_E_SHAPE;
+  const long total = (long)B * (H / stride) * (W / stride);
+  conv3x3_c3_fwd_kernel<64><<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, (bf16*)y, B,
+                                                                                         H, W, stride);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_conv3x3_c3_wgrad(const void* dy, const float* x_nchw, float* dw, float* db, int B, int H, int W, int cout,
+                         int stride, void* stream) {
+  if (cout != 64) return LUN_E_SHAPE;
+  conv3x3_c3_wgrad_kernel<64><<<148 * 2, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, x_nchw, dw, db, B, H, W,
+                                                                        stride);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_final_conv_tanh_fwd(const void* x, const float* w, const float* bias, float* recon, int B, int H, int W,
+                            void* stream) {
+  const long total = (long)B * H * W;
+  final_conv_tanh_fwd_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias,
+                                                                                          recon, B, H, W);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_final_conv_bwd(const float* drecon, const float* recon, const void* x, const float* w, void* dx, float* dw,
+                       float* db, int B, int H, int W, void* stream) {
+  if (H % 16 || W % 16) return LUN_E_SHAPE;
+  const long total = (long)B * H * W;
+  final_conv_dgrad_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(drecon, recon, w, (bf16*)dx, B,
+                                                                                       H, W);
+  dim3 grid(W / 16, H / 16, B);
+  final_conv_wgrad_kernel<<<grid, 320, 0, (cudaStream_t)stream>>>(drecon, recon, (const bf16*)x, dw, db, H, W);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_reparam_fwd(const float* mulv, const float* eps, void* z, int B, int L, void* stream) {
+  reparam_fwd_kernel<<<(B * L + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mulv, eps, (bf16*)z, B, L);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_reparam_bwd(const float* mulv, const float* eps, const void* dz, const float* dmu, const float* dlogvar,
+                    void* dmulv, int B, int L, void* stream) {
+  reparam_bwd_kernel<<<(B * L + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mulv, eps, (const bf16*)dz, dmu, dlogvar,
+                                                                            (bf16*)dmulv, B, L);
+  return LUN_LAUNCH_OK();
+}
+
+}  // extern "C"

@@ -109,7 +109,7 @@ def local_attention(qkv, semantics="reference", attn_mask=None):
     if semantics == "intended":
         out = o.reshape(B, HEADS, N, hd)
     else:
-        out = torch.zeros(B, HEADS, N, hd, dtype=qkv.dtype)
+        out = torch.zeros(B, HEADS, N, hd, dtype=o.dtype, device=qkv.device)
         out[:, :, :nc] = o[:, :, :, 0]
         out[:, :, nc - 1: nc - 1 + CHUNK] = o[:, :, nc - 1]
     return out.permute(0, 1, 3, 2).reshape(B, C, H, W)                       # :223
@@ -142,6 +142,23 @@ def expert_block(x, sd, p, training, semantics, masks, mkey, bn_updates, grad_mo
     return F.leaky_relu(h + identity, 0.2)
 
 
+def teacher_trunk(x, sd, training=True, semantics="reference", grad_mode="reference", masks=None,
+                  no_grad_pass=False, num_experts=4, expert_layers=3):
+    """Feature extractor + the expert stacks (lunar_evaluator.py:411-424): returns (features, [expert outputs])."""
+    fe = feature_extractor(x, sd, training, masks, 1)
+    if grad_mode == "reference" and training:
+        fe = fe.detach()                                                         # rule (i)
+    outs = []
+    for e in range(num_experts):
+        h = fe
+        for b in range(expert_layers):
+            p = f"experts.{e}.{b}"
+            recomputed = training and not no_grad_pass and grad_mode == "reference" and h.requires_grad
+            h = expert_block(h, sd, p, training, semantics, masks, p, 2 if recomputed else 1, grad_mode)
+        outs.append(h)
+    return fe, outs
+
+
 def teacher_forward(x, sd, training=True, semantics="reference", grad_mode="reference", masks=None,
                     no_grad_pass=False, num_experts=4, expert_layers=3):
     """LunarMoETeacher.forward (lunar_evaluator.py:409-462) on state_dict `sd` (BN buffers updated in place).
@@ -151,21 +168,12 @@ def teacher_forward(x, sd, training=True, semantics="reference", grad_mode="refe
     training=True, no_grad_pass=False: pass B; BNs of blocks whose checkpoint segment is re-run in backward
                                         (blocks 1,2 in reference grad mode) are updated twice.
     Returns the reference's output dict plus 'quality_logits' / 'semantic_logit' (pre-sigmoid, for tolerances)."""
-    fe = feature_extractor(x, sd, training, masks, 1)
-    if grad_mode == "reference" and training:
-        fe = fe.detach()                                                         # rule (i)
+    fe, outs = teacher_trunk(x, sd, training, semantics, grad_mode, masks, no_grad_pass, num_experts, expert_layers)
     pooled_fe = fe.mean((2, 3))
     gate_logits = _mlp_head(pooled_fe, sd, "gate", False, masks, "gate_drop")
     weights = gate_logits.softmax(1)
-    outs, quals = [], []
-    for e in range(num_experts):
-        h = fe
-        for b in range(expert_layers):
-            p = f"experts.{e}.{b}"
-            recomputed = training and not no_grad_pass and grad_mode == "reference" and h.requires_grad
-            h = expert_block(h, sd, p, training, semantics, masks, p, 2 if recomputed else 1, grad_mode)
-        outs.append(h)
-        quals.append(_mlp_head(h.mean((2, 3)), sd, f"quality_heads.{e}", True, masks, f"quality_drop.{e}"))
+    quals = [_mlp_head(outs[e].mean((2, 3)), sd, f"quality_heads.{e}", True, masks, f"quality_drop.{e}")
+             for e in range(num_experts)]
     qt = torch.stack(quals, 1)
     wq = (qt * weights.unsqueeze(-1)).sum(1)
     comb = (torch.stack([o.mean((2, 3)) for o in outs], 1) * weights.unsqueeze(-1)).sum(1)
