@@ -33,6 +33,8 @@ extern "C" {
 int lun_num_sms(void);
 /* ABI version of this header. */
 int lun_abi_version(void);
+/* Number of kernels this library has launched in the calling process (monotonic). */
+long long lun_launch_count(void);
 
 /* Implicit-GEMM convolution in tap-list form (tcgen05 + TMA).  out[b, h*o_mul+o_ph, w*o_mul+o_pw, o_coff+n] =
  *   epi( sum_t sum_c x[b, h*in_mul+dy[t], w*in_mul+dx[t], c] * w_packed[slab[t]][n][c] )   for (b,h,w) in [GB,GH,GW]

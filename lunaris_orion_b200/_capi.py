@@ -47,6 +47,7 @@ c_int_p = ctypes.POINTER(ctypes.c_int)
 SIGNATURES = {
     "lun_num_sms": [],
     "lun_abi_version": [],
+    "lun_launch_count": [],
     "lun_conv_taps_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                            c_int, c_int, c_int, c_int, c_int, c_int_p, c_int_p, c_int_p,
                            c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -91,7 +92,7 @@ def _declare(l):
     for name, argtypes in SIGNATURES.items():
         fn = getattr(l, name)
         fn.argtypes = argtypes
-        fn.restype = c_int
+        fn.restype = ctypes.c_longlong if name == "lun_launch_count" else c_int
 
 
 def check(rc, what):

@@ -1,6 +1,8 @@
 // extern "C" surface of liblunaris_b200.so (declared in include/lunaris_b200.h).
 #include "../../include/lunaris_b200.h"
 #include "conv_gemm.cuh"
+#include "launch_count.cuh"
+#include <atomic>
 
 namespace lun {
 int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, int nslabs, ConvGeom g,
@@ -8,12 +10,15 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
 int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int XB, int XH, int XW, WgradGeom g,
                       float* dw, cudaStream_t stream);
 int num_sms();
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace lun
 
 extern "C" {
 
 int lun_abi_version(void) { return 1; }
 int lun_num_sms(void) { return lun::num_sms(); }
+long long lun_launch_count(void) { return lun::g_launches.load(); }
 
 int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const void* w_packed, int nslabs, int Cout,
                        int GB, int GH, int GW, int in_mul, int ntaps, const int* dy, const int* dx, const int* slab,

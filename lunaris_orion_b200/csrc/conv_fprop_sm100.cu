@@ -15,6 +15,7 @@
 // lunar_generate.py:36,41,95-116,169-187) and their autograd data-gradients.
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
+#include "launch_count.cuh"
 
 namespace lun {
 
@@ -402,6 +403,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   int grid = num_sms();
   if (grid > total_tiles) grid = total_tiles;
   conv_fprop_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmO, g, bias, out, stats);
+  note_launch(1);
   return cudaGetLastError() == cudaSuccess ? 0 : 9;
 }
 

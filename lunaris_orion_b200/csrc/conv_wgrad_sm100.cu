@@ -11,6 +11,7 @@
 // (lunar_evaluator.py:249,134,255; lunar_generate.py:36,41,95-116,169-187).
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
+#include "launch_count.cuh"
 
 namespace lun {
 
@@ -238,6 +239,7 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
   int grid = num_sms();
   if (grid > tiles * splits) grid = tiles * splits;
   conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, g, dw);
+  note_launch(1);
   return cudaGetLastError() == cudaSuccess ? 0 : 9;
 }
 

@@ -7,6 +7,7 @@
 // :241-258 (ExpertBlock conv->LeakyReLU->BN->Dropout2d, layer_scale), :260-275 (residual + leaky_relu).
 #include "../../include/lunaris_b200.h"
 #include "elem_common.cuh"
+#include "launch_count.cuh"
 
 namespace lun {
 
@@ -454,6 +455,7 @@ int lun_channel_stats_bf16(const void* x, long P, int C, float* stats, void* str
   if (blocks > 148 * 8) blocks = 148 * 8;
   channel_stats_kernel<<<(int)blocks, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)x, stats, P, C);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
@@ -463,6 +465,7 @@ int lun_bn_finalize(const float* stats, double n, const float* gamma, const floa
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, n, gamma, beta, running_mean,
                                                                        running_var, num_batches_tracked, n_updates,
                                                                        momentum, eps, scale, shift, mean, rstd, C);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
@@ -479,6 +482,7 @@ int lun_affine_fwd_bf16(const void* x, const float* scale, const float* shift, c
   const int lanes = kEThreads / (C / 8);
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
   affine_fwd_kernel<<<grid, kEThreads, pool ? lanes * C * sizeof(float) : 0, (cudaStream_t)stream>>>(a);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
@@ -493,6 +497,7 @@ int lun_block_bwd_reduce_bf16(const void* dout, const float* gpool, const void* 
   const int lanes = kEThreads / (C / 8);
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
   blk_bwd_reduce_kernel<<<grid, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(a);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
@@ -509,6 +514,7 @@ int lun_block_bwd_apply_bf16(const void* dpre, const float* gpool, const void* o
   const int lanes = kEThreads / (C / 8);
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
   blk_bwd_apply_kernel<<<grid, kEThreads, dbias ? lanes * C * sizeof(float) : 0, (cudaStream_t)stream>>>(a);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
@@ -522,6 +528,7 @@ int lun_attn_ref_rows_bf16(const void* qkv, void* att_small, int B, int N, int C
   const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   attn_ref_rows_kernel<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)qkv, (bf16*)att_small, B, N, C, heads, nq_pad, seed, th, ds);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
@@ -533,6 +540,7 @@ int lun_proj_expand_bf16(const void* proj_small, const float* bias, void* y, int
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
   proj_expand_kernel<<<grid, kEThreads, 0, (cudaStream_t)stream>>>((const bf16*)proj_small, bias, (bf16*)y, B, HW, C,
                                                                   nq, nq_pad, seed, th, ds);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
@@ -545,6 +553,7 @@ int lun_proj_bwd_gather_bf16(const void* dh2, void* dpo_small, float* dbias, int
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
   proj_bwd_gather_kernel<<<grid, kEThreads, lanes * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)dh2, (bf16*)dpo_small, dbias, B, HW, C, nq, nq_pad, seed, th, ds);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 

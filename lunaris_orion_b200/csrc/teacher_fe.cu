@@ -5,6 +5,7 @@
 // Arithmetic mirrors the reference's bf16 autocast: conv operands rounded to bf16, fp32 accumulate, bf16 results.
 #include "../../include/lunaris_b200.h"
 #include "elem_common.cuh"
+#include "launch_count.cuh"
 
 namespace lun {
 
@@ -185,6 +186,7 @@ int lun_fe_conv1(const float* x_nchw, const float* w, const float* bias, void* y
   const long total = (long)B * H * W;
   fe_conv1_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, (bf16*)y, stats, B,
                                                                                H, W, slope);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
@@ -206,6 +208,7 @@ int lun_fe_branches(const void* y0, const float* scale, const float* shift, cons
   dim3 grid(W / kT, H / kT, B);
   fe_branch_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)y0, scale, shift, wt, (bf16*)cat, H, W,
                                                              slope);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 

@@ -3,6 +3,7 @@
 // and the reparameterisation. Activations are NHWC bf16 [B, HW, C]; images are NCHW fp32 as the trainer hands them.
 #include "../../include/lunaris_b200.h"
 #include "elem_common.cuh"
+#include "launch_count.cuh"
 
 namespace lun {
 
@@ -489,6 +490,7 @@ int lun_image_channel_stats_bf16(const void* x, float* stats, int B, int HW, int
   dim3 grid(vae_blocks(HW, C, B), B);
   image_channel_stats_kernel<<<grid, kVT, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x,
                                                                                                  stats, HW, C);
+  lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }
 
@@ -498,6 +500,7 @@ int lun_gn_mish_fwd_bf16(const void* x, const float* stats, const float* gamma, 
   dim3 grid(vae_blocks(HW, C, B), B);
   gn_mish_fwd_kernel<<<grid, kVT, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, gamma, beta, (const bf16*)res,
                                                              (const bf16*)add, (bf16*)y, HW, C, groups, eps);
+  lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }
 
@@ -513,6 +516,7 @@ int lun_gn_mish_bwd_bf16(const void* dy, const void* dy2, const void* x, const f
   gn_mish_bwd_kernel<1><<<grid, kVT, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)x,
                                                                 stats, gamma, beta, (const bf16*)res, red, (bf16*)dx,
                                                                 (bf16*)dres, HW, C, groups, eps);
+  lun::note_launch(2);
   return LUN_LAUNCH_OK();
 }
 
@@ -522,6 +526,7 @@ int lun_conv3x3_c3_fwd(const float* x_nchw, const float* w, const float* bias, v
   const long total = (long)B * (H / stride) * (W / stride);
   conv3x3_c3_fwd_kernel<64><<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, (bf16*)y, B,
                                                                                          H, W, stride);
+  lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }
 
@@ -530,6 +535,7 @@ int lun_conv3x3_c3_wgrad(const void* dy, const float* x_nchw, float* dw, float* 
   if (cout != 64) return LUN_E_SHAPE;
   conv3x3_c3_wgrad_kernel<64><<<148 * 2, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, x_nchw, dw, db, B, H, W,
                                                                         stride);
+  lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }
 
@@ -538,6 +544,7 @@ int lun_final_conv_tanh_fwd(const void* x, const float* w, const float* bias, fl
   const long total = (long)B * H * W;
   final_conv_tanh_fwd_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias,
                                                                                           recon, B, H, W);
+  lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }
 
@@ -549,11 +556,13 @@ int lun_final_conv_bwd(const float* drecon, const float* recon, const void* x, c
                                                                                        H, W);
   dim3 grid(W / 16, H / 16, B);
   final_conv_wgrad_kernel<<<grid, 320, 0, (cudaStream_t)stream>>>(drecon, recon, (const bf16*)x, dw, db, H, W);
+  lun::note_launch(2);
   return LUN_LAUNCH_OK();
 }
 
 int lun_reparam_fwd(const float* mulv, const float* eps, void* z, int B, int L, void* stream) {
   reparam_fwd_kernel<<<(B * L + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mulv, eps, (bf16*)z, B, L);
+  lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }
 
@@ -561,6 +570,7 @@ int lun_reparam_bwd(const float* mulv, const float* eps, const void* dz, const f
                     void* dmulv, int B, int L, void* stream) {
   reparam_bwd_kernel<<<(B * L + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mulv, eps, (const bf16*)dz, dmu, dlogvar,
                                                                             (bf16*)dmulv, B, L);
+  lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }
 
