@@ -1,0 +1,83 @@
+"""One hybrid step through lunaris_orion_b200.train_hybrid.TrainingManager on the GPU vs (a) the 12 metrics of the
+real reference trainer stored in tests/golden, (b) the CPU oracle, plus checkpoint layout / resume and LR schedule."""
+import os
+
+import pytest
+import torch
+
+import teacher_cases as tc
+from oracle import restatement as R
+
+gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.pt"),
+                  weights_only=False)
+CFG = gold["cfg"]
+
+
+def _manager(dev, tmp_path, extra=()):
+    from lunaris_orion_b200.train_hybrid import TrainingManager, build_arg_parser
+    args = build_arg_parser().parse_args([
+        "--data_dir", "synthetic", "--output_dir", str(tmp_path), "--batch_size", str(CFG["B"]),
+        "--gradient_accumulation_steps", "1", "--latent_dim", str(CFG["latent"]), "--embedding_dim", str(CFG["emb"]),
+        "--feature_dim", str(CFG["feat"]), "--seed", "42", *extra])
+    tm = TrainingManager(args, device=dev)
+    for m in tm.teacher.modules():
+        if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout2d)):
+            m.p = 0.0
+    return tm
+
+
+@pytest.mark.gpu
+def test_step_metrics_match_reference_trainer_golden(cuda_dev, tmp_path):
+    tm = _manager(cuda_dev, tmp_path)
+    x = tc.images(CFG["B"], CFG["img_seed"]).to(cuda_dev)
+    torch.manual_seed(gold["trainer_step"]["eps_seed"])
+    m = tm._process_batch(x, 0)
+    ref = gold["trainer_step"]["metrics"]
+    # bf16 tolerance: losses 3 % relative; quality / semantic outputs are sigmoid values of ill-conditioned heads
+    for k in ("recon_loss", "kl_loss", "vae_loss"):
+        assert abs(m[k] - ref[k]) <= 0.03 * abs(ref[k]) + 1e-4, (k, m[k], ref[k])
+    for k in ("quality_scores", "quality_reward", "quality_loss"):
+        assert abs(m[k] - ref[k]) <= 0.05, (k, m[k], ref[k])
+    assert abs(m["advantage"]) < 1e-6 and abs(m["pg_loss"]) < 1e-6           # first step: baseline == reward mean
+    none = sorted(n for n, p in tm.teacher.named_parameters() if p.grad is None)
+    assert none == gold["trainer_step"]["teacher_none"]
+    assert all(p.grad is not None for p in tm.vae.parameters())
+    sd = tm.teacher.state_dict()
+    for k, v in gold["trainer_step"]["teacher_nbt"].items():
+        assert int(sd[k]) == v, k
+    assert abs(tm.vae_optimizer.param_groups[0]["lr"] - gold["trainer_step"]["vae_lr"]) < 1e-12
+    tm._process_batch(x, 1)
+    assert abs(tm.vae_optimizer.param_groups[0]["lr"] - gold["trainer_step2"]["vae_lr"]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_checkpoint_layout_and_resume(cuda_dev, tmp_path):
+    tm = _manager(cuda_dev, tmp_path)
+    x = tc.images(CFG["B"], 11).to(cuda_dev)
+    tm._process_batch(x, 0)
+    path = tm._save_checkpoint()
+    ck = torch.load(path, weights_only=True)
+    assert sorted(ck.keys()) == gold["checkpoint_keys"]
+    assert sorted(ck["args"].keys()) == gold["checkpoint_args_keys"]
+    assert list(ck["teacher_state_dict"].keys()) == gold["teacher_keys_after_forward"]
+    assert list(ck["vae_state_dict"].keys()) == gold["vae_keys"]
+    tm2 = _manager(cuda_dev, tmp_path, extra=("--resume_from", path))
+    assert tm2.global_step == 1
+    for (k, a), (_, b) in zip(tm.vae.state_dict().items(), tm2.vae.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert abs(tm2.vae_optimizer.param_groups[0]["lr"] - tm.vae_optimizer.param_groups[0]["lr"]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_grad_accumulation_quirk(cuda_dev, tmp_path):
+    """--gradient_accumulation_steps 2: no optimizer step on the first micro-batch, grads zeroed each micro-batch and
+    scaled by 1/2."""
+    tm = _manager(cuda_dev, tmp_path)
+    tm.args.gradient_accumulation_steps = 2
+    x = tc.images(CFG["B"], 12).to(cuda_dev)
+    w0 = tm.vae.decoder.final_conv.weight.detach().clone()
+    m = tm._process_batch(x, 0)
+    assert torch.equal(w0, tm.vae.decoder.final_conv.weight.detach())
+    assert abs(m["vae_loss"] * 2 - (m["recon_loss"] + 0.1 * m["kl_loss"] + m["pg_loss"])) < 1e-4
+    tm._process_batch(x, 1)
+    assert not torch.equal(w0, tm.vae.decoder.final_conv.weight.detach())

@@ -1,0 +1,84 @@
+"""GPU parity of the Teacher path (lunaris_orion_b200.lunar_evaluator through the C ABI) against the CPU oracle.
+
+Tolerances: the kernels compute in bf16 with fp32 accumulation, like the reference under bf16 autocast. Every check
+is therefore calibrated against how far a bf16-autocast execution of the reference's own op sequence (the oracle
+run under torch.autocast on the same GPU) drifts from the fp32 oracle: ours must stay within 3x that drift plus a
+small floor (stated per assertion)."""
+import os
+
+import pytest
+import torch
+
+import teacher_cases as tc
+
+gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.pt"),
+                  weights_only=False)
+
+
+@pytest.mark.gpu
+def test_teacher_eval_matches_oracle(cuda_dev):
+    rep = tc.eval_report(cuda_dev)
+    assert rep["expert_weights"] < 5e-3            # relative to max |ref|
+    assert rep["style_embedding"] < 2e-2 and rep["prompt_embedding"] < 2e-2
+    assert rep["feature_maps"] < 3e-2
+    assert rep["quality_logit_abs"] < 0.03 * rep["quality_logit_scale"] + 0.02
+
+
+@pytest.mark.gpu
+def test_teacher_trunk_forward_backward_within_bf16_calibration(cuda_dev):
+    rep = tc.trunk_report(cuda_dev)
+    assert rep["grad_keys_equal"]
+    assert rep["pool"] <= 3 * rep["cal_pool"] + 2e-3
+    assert rep["grad_rel_max"] <= 3 * rep["cal_grad_rel_max"] + 0.02, rep["grad_worst"]
+
+
+@pytest.mark.gpu
+def test_teacher_train_gradient_set_and_bn_counters(cuda_dev):
+    rep = tc.train_report(cuda_dev)
+    assert rep["none_set_equal"] and rep["n_none"] == 168
+    assert rep["quality_logit_abs"] < 0.15 * rep["quality_logit_scale"]     # ill-conditioned heads at B=2
+
+
+@pytest.mark.gpu
+def test_teacher_eval_matches_reference_golden(cuda_dev):
+    """Against outputs of the REAL reference (tests/golden, made by oracle/make_golden.py)."""
+    cfg = gold["cfg"]
+    from lunaris_orion_b200 import lunar_evaluator as le
+    torch.manual_seed(cfg["seed"])
+    from lunaris_orion_b200 import lunar_generate as lg
+    lg.LunarisCoreVAE(latent_dim=cfg["latent"])            # same RNG consumption order as the golden script
+    t = le.LunarMoETeacher(feature_dim=cfg["feat"], embedding_dim=cfg["emb"], dropout_rate=0.0).to(cuda_dev).eval()
+    with torch.no_grad():
+        out = t(tc.images(cfg["B"], cfg["img_seed"]).to(cuda_dev))
+    ref = gold["teacher_eval"]
+    assert tc.rel_err(out["expert_weights"], ref["expert_weights"]) < 5e-3
+    assert tc.rel_err(out["style_embedding"], ref["style_embedding"]) < 2e-2
+    assert (tc.logit(out["quality_scores"]) - tc.logit(ref["quality_scores"])).abs().max().item() < 0.1
+    assert len(t.state_dict()) == len(gold["teacher_keys_after_forward"]) == 391
+
+
+@pytest.mark.gpu
+def test_dropout_kernels_statistics_and_replay(cuda_dev):
+    """Elementwise dropout: keep-rate ~ 1-p, survivors scaled by bf16(1/(1-p)), and the backward replays the mask."""
+    import ctypes
+    from lunaris_orion_b200 import _capi
+    lib = _capi.lib()
+    B, HW, C, nq, nq_pad, p, seed = 2, 4096, 64, 159, 160, 0.1, 12345
+    small = torch.ones(B, nq_pad, C, device=cuda_dev, dtype=torch.bfloat16)
+    bias = torch.ones(C, device=cuda_dev)
+    y = torch.empty(B, HW, C, device=cuda_dev, dtype=torch.bfloat16)
+    s = torch.cuda.current_stream().cuda_stream
+    _capi.check(lib.lun_proj_expand_bf16(small.data_ptr(), bias.data_ptr(), y.data_ptr(), B, HW, C, nq, nq_pad, seed,
+                                         ctypes.c_float(p), s), "expand")
+    yf = y.float()
+    keep = (yf != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 5e-3
+    assert torch.allclose(yf[yf != 0], torch.tensor(1.109375, device=cuda_dev))
+    dpo = torch.zeros(B, nq_pad, C, device=cuda_dev, dtype=torch.bfloat16)
+    db = torch.zeros(C, device=cuda_dev)
+    ones = torch.ones(B, HW, C, device=cuda_dev, dtype=torch.bfloat16)
+    _capi.check(lib.lun_proj_bwd_gather_bf16(ones.data_ptr(), dpo.data_ptr(), db.data_ptr(), B, HW, C, nq, nq_pad, seed,
+                                             ctypes.c_float(p), s), "gather")
+    torch.cuda.synchronize()
+    assert torch.equal(dpo[:, :nq].float(), yf[:, :nq])                       # same mask as the forward
+    assert torch.allclose(db, yf.sum((0, 1)), rtol=1e-3)
