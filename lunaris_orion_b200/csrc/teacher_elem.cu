@@ -12,12 +12,31 @@
 namespace lun {
 
 constexpr int kEThreads = 256;
+constexpr int kUR = 2;  // three input streams in the backward reduce pass
+constexpr int kU = 4;   // pixels per thread per iteration: all loads are issued before any is consumed
 
 struct ChanGeom {
   int cg;      // channel groups of 8
   int lanes;   // pixel lanes per block
   __device__ __forceinline__ ChanGeom(int C) : cg(C >> 3), lanes(kEThreads / (C >> 3)) {}
 };
+
+
+// 16-byte packed bf16 vector <-> 8 floats (kept packed while loads are in flight to save registers)
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void lds8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 
 // sums[k][c] partial per thread -> block reduce -> atomicAdd(dst_k[c]). NS = number of statistics.
 template <int NS>
@@ -49,13 +68,22 @@ __global__ void __launch_bounds__(kEThreads) channel_stats_kernel(const bf16* __
   const bool active = lane_px < g.lanes;
   float acc[2][8] = {};
   if (active) {
-    for (long p = (long)blockIdx.x * g.lanes + lane_px; p < P; p += (long)gridDim.x * g.lanes) {
-      float v[8];
-      load8(x + p * C + cgi * 8, v);
+    for (long p0 = (long)blockIdx.x * g.lanes * kU + lane_px; p0 < P; p0 += (long)gridDim.x * g.lanes * kU) {
+      float vv[kU][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += v[j];
-        acc[1][j] += v[j] * v[j];
+      for (int u = 0; u < kU; ++u) {
+        const long p = p0 + (long)u * g.lanes;
+        if (p < P) load8(x + p * C + cgi * 8, vv[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const long p = p0 + (long)u * g.lanes;
+        if (p >= P) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += vv[u][j];
+          acc[1][j] += vv[u][j] * vv[u][j];
+        }
       }
     }
   }
@@ -114,64 +142,91 @@ struct AffineArgs {
   float slope;            // leaky slope applied after the residual add when idn != null
 };
 
-__global__ void __launch_bounds__(kEThreads) affine_fwd_kernel(const AffineArgs a) {
-  extern __shared__ float smem[];
+__global__ void __launch_bounds__(kEThreads, 3) affine_fwd_kernel(const AffineArgs a) {
+  extern __shared__ __align__(16) float smem[];
   const ChanGeom g(a.C);
+  const int C = a.C;
+  float* sP = smem;                       // [6][C]: scale, shift, m2, ls, id_scale, id_shift
+  float* sRed = smem + 6 * C;             // [lanes][C] pooling partials
   const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
   const bool active = lane_px < g.lanes;
   const int b = blockIdx.y;
   const int c0 = cgi * 8;
-  float sc[8], sh[8], m2[8], ls[8], isc[8], ish[8];
+  for (int c = threadIdx.x; c < C; c += kEThreads) {
+    sP[c] = a.scale ? a.scale[c] : 1.f;
+    sP[C + c] = a.shift ? a.shift[c] : 0.f;
+    sP[2 * C + c] = a.m2 ? a.m2[(size_t)b * C + c] : 1.f;
+    sP[3 * C + c] = a.ls ? a.ls[c] : 1.f;
+    sP[4 * C + c] = a.id_scale ? a.id_scale[c] : 1.f;
+    sP[5 * C + c] = a.id_scale ? a.id_shift[c] : 0.f;
+  }
+  __syncthreads();
   float acc[1][8] = {};
   if (active) {
+    for (int p0 = blockIdx.x * g.lanes * kU + lane_px; p0 < a.HW; p0 += gridDim.x * g.lanes * kU) {
+      uint4 xr[kU], ir[kU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = a.scale ? a.scale[c0 + j] : 1.f;
-      sh[j] = a.shift ? a.shift[c0 + j] : 0.f;
-      m2[j] = a.m2 ? a.m2[(size_t)b * a.C + c0 + j] : 1.f;
-      ls[j] = a.ls ? a.ls[c0 + j] : 1.f;
-      isc[j] = a.id_scale ? a.id_scale[c0 + j] : 1.f;
-      ish[j] = a.id_scale ? a.id_shift[c0 + j] : 0.f;
-    }
-    for (int p = blockIdx.x * g.lanes + lane_px; p < a.HW; p += gridDim.x * g.lanes) {
-      const size_t off = ((size_t)b * a.HW + p) * a.C + c0;
-      float v[8];
-      load8(a.x + off, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = rbf(v[j] * sc[j] + sh[j]);
-        if (a.m2) v[j] = rbf(v[j] * m2[j]);
-      }
-      if (a.thresh16) {
-        bool keep[8];
-        drop_keep8(a.seed, off >> 3, a.thresh16, keep);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = keep[j] ? rbf(v[j] * a.drop_scale) : 0.f;
-      }
-      if (a.ls) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= ls[j];
-      }
-      if (a.idn) {
-        float iv[8];
-        load8(a.idn + off, iv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float id = a.id_scale ? rbf(iv[j] * isc[j] + ish[j]) : iv[j];
-          const float s = v[j] + id;
-          v[j] = s > 0.f ? s : s * a.slope;
+      for (int u = 0; u < kU; ++u) {
+        const int p = p0 + u * g.lanes;
+        if (p < a.HW) {
+          const size_t off = ((size_t)b * a.HW + p) * C + c0;
+          xr[u] = ldg16(a.x + off);
+          if (a.idn) ir[u] = ldg16(a.idn + off);
         }
       }
-      store8(a.y + off, v);
-      if (a.pool) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+      for (int u = 0; u < kU; ++u) {
+        const int p = p0 + u * g.lanes;
+        if (p >= a.HW) continue;
+        const size_t off = ((size_t)b * a.HW + p) * C + c0;
+        float v[8], t0[8], t1[8];
+        unpack8(xr[u], v);
+        lds8(sP + c0, t0);
+        lds8(sP + C + c0, t1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = rbf(v[j] * t0[j] + t1[j]);
+        if (a.m2) {
+          lds8(sP + 2 * C + c0, t0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = rbf(v[j] * t0[j]);
+        }
+        if (a.thresh16) {
+          bool keep[8];
+          drop_keep8(a.seed, off >> 3, a.thresh16, keep);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = keep[j] ? rbf(v[j] * a.drop_scale) : 0.f;
+        }
+        if (a.ls) {
+          lds8(sP + 3 * C + c0, t0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= t0[j];
+        }
+        if (a.idn) {
+          float iv[8];
+          unpack8(ir[u], iv);
+          if (a.id_scale) {
+            lds8(sP + 4 * C + c0, t0);
+            lds8(sP + 5 * C + c0, t1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) iv[j] = rbf(iv[j] * t0[j] + t1[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float sum = v[j] + iv[j];
+            v[j] = sum > 0.f ? sum : sum * a.slope;
+          }
+        }
+        store8(a.y + off, v);
+        if (a.pool) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+        }
       }
     }
   }
   if (a.pool) {
-    float* const dst[1] = {a.pool + (size_t)b * a.C};
-    block_channel_reduce<1>(acc, smem, a.C, lane_px, cgi, active, dst);
+    float* const dst[1] = {a.pool + (size_t)b * C};
+    block_channel_reduce<1>(acc, sRed, C, lane_px, cgi, active, dst);
   }
 }
 
@@ -191,48 +246,72 @@ struct BlkBwdArgs {
   float slope_out;
 };
 
-__global__ void __launch_bounds__(kEThreads) blk_bwd_reduce_kernel(const BlkBwdArgs a) {
-  extern __shared__ float smem[];
+__global__ void __launch_bounds__(kEThreads, 3) blk_bwd_reduce_kernel(const BlkBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
   const ChanGeom g(a.C);
+  const int C = a.C;
+  float* sP = smem;                       // [4][C]: mean, rstd, m2, gpool
+  float* sRed = smem + 4 * C;             // [lanes][2][C]
   const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
   const bool active = lane_px < g.lanes;
   const int b = blockIdx.y, c0 = cgi * 8;
+  for (int c = threadIdx.x; c < C; c += kEThreads) {
+    sP[c] = a.mean[c];
+    sP[C + c] = a.rstd[c];
+    sP[2 * C + c] = a.m2 ? a.m2[(size_t)b * C + c] : 1.f;
+    sP[3 * C + c] = a.gpool ? a.gpool[(size_t)b * C + c] : 0.f;
+  }
+  __syncthreads();
   float acc[2][8] = {};
   if (active) {
-    float mean[8], rstd[8], m2[8], gp[8];
+    for (int p0 = blockIdx.x * g.lanes * kUR + lane_px; p0 < a.HW; p0 += gridDim.x * g.lanes * kUR) {
+      uint4 dr[kUR], ar[kUR], orr[kUR];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mean[j] = a.mean[c0 + j];
-      rstd[j] = a.rstd[c0 + j];
-      m2[j] = a.m2 ? a.m2[(size_t)b * a.C + c0 + j] : 1.f;
-      gp[j] = a.gpool ? a.gpool[(size_t)b * a.C + c0 + j] : 0.f;
-    }
-    for (int p = blockIdx.x * g.lanes + lane_px; p < a.HW; p += gridDim.x * g.lanes) {
-      const size_t off = ((size_t)b * a.HW + p) * a.C + c0;
-      float d[8], av[8];
-      if (a.dout) load8(a.dout + off, d);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = gp[j];
+      for (int u = 0; u < kUR; ++u) {
+        const int p = p0 + u * g.lanes;
+        if (p < a.HW) {
+          const size_t off = ((size_t)b * a.HW + p) * C + c0;
+          if (a.dout) dr[u] = ldg16(a.dout + off);
+          if (a.out) orr[u] = ldg16(a.out + off);
+          ar[u] = ldg16(a.a + off);
+        }
       }
-      if (a.out) {
-        float o[8];
-        load8(a.out + off, o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : d[j] * a.slope_out;
-      }
-      if (a.dpre) store8(a.dpre + off, d);
-      load8(a.a + off, av);
+      for (int u = 0; u < kUR; ++u) {
+        const int p = p0 + u * g.lanes;
+        if (p >= a.HW) continue;
+        const size_t off = ((size_t)b * a.HW + p) * C + c0;
+        float d[8], t0[8], t1[8];
+        if (a.dout) unpack8(dr[u], d);
+        else lds8(sP + 3 * C + c0, d);
+        if (a.out) {
+          unpack8(orr[u], t0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dm = (a.dpre ? rbf(d[j]) : d[j]) * m2[j];
-        acc[0][j] += dm;
-        acc[1][j] += dm * (av[j] - mean[j]) * rstd[j];
+          for (int j = 0; j < 8; ++j) d[j] = t0[j] > 0.f ? d[j] : d[j] * a.slope_out;
+        }
+        if (a.dpre) {
+          store8(a.dpre + off, d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = rbf(d[j]);
+        }
+        lds8(sP + 2 * C + c0, t0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] *= t0[j];
+        unpack8(ar[u], t0);
+        lds8(sP + c0, t1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t0[j] -= t1[j];
+        lds8(sP + C + c0, t1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += d[j];
+          acc[1][j] += d[j] * t0[j] * t1[j];
+        }
       }
     }
   }
   float* const dst[2] = {a.t1, a.t2};
-  block_channel_reduce<2>(acc, smem, a.C, lane_px, cgi, active, dst);
+  block_channel_reduce<2>(acc, sRed, C, lane_px, cgi, active, dst);
 }
 
 struct BlkBwdApplyArgs {
@@ -252,59 +331,85 @@ struct BlkBwdApplyArgs {
   float inv_n;          // 1 / (B*HW)
 };
 
-__global__ void __launch_bounds__(kEThreads) blk_bwd_apply_kernel(const BlkBwdApplyArgs a) {
-  extern __shared__ float smem[];
+__global__ void __launch_bounds__(kEThreads, 3) blk_bwd_apply_kernel(const BlkBwdApplyArgs a) {
+  extern __shared__ __align__(16) float smem[];
   const ChanGeom g(a.C);
+  const int C = a.C;
+  float* sP = smem;                       // [7][C]: mean, rstd, gm, s1, s2, k0, gpool
+  float* sRed = smem + 7 * C;             // [lanes][C]
   const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
   const bool active = lane_px < g.lanes;
   const int b = blockIdx.y, c0 = cgi * 8;
+  for (int c = threadIdx.x; c < C; c += kEThreads) {
+    const float ls = a.ls ? a.ls[c] : 1.f;
+    const float rstd = a.rstd[c];
+    sP[c] = a.mean[c];
+    sP[C + c] = rstd;
+    sP[2 * C + c] = ls * (a.m2 ? a.m2[(size_t)b * C + c] : 1.f);   // g = dpre * gm
+    sP[3 * C + c] = ls * a.t1[c] * a.inv_n;
+    sP[4 * C + c] = ls * a.t2[c] * a.inv_n;
+    sP[5 * C + c] = a.gamma[c] * rstd;
+    sP[6 * C + c] = a.gpool ? a.gpool[(size_t)b * C + c] : 0.f;
+  }
+  __syncthreads();
   float acc[1][8] = {};
   if (active) {
-    float mean[8], rstd[8], k0[8], s1[8], s2[8], gp[8], gm[8];
+    for (int p0 = blockIdx.x * g.lanes * kU + lane_px; p0 < a.HW; p0 += gridDim.x * g.lanes * kU) {
+      uint4 dr[kU], ar[kU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float ls = a.ls ? a.ls[c] : 1.f;
-      mean[j] = a.mean[c];
-      rstd[j] = a.rstd[c];
-      gm[j] = ls * (a.m2 ? a.m2[(size_t)b * a.C + c] : 1.f);   // g = dpre * gm
-      s1[j] = ls * a.t1[c] * a.inv_n;
-      s2[j] = ls * a.t2[c] * a.inv_n;
-      k0[j] = a.gamma[c] * rstd[j];
-      gp[j] = a.gpool ? a.gpool[(size_t)b * a.C + c] : 0.f;
-    }
-    for (int p = blockIdx.x * g.lanes + lane_px; p < a.HW; p += gridDim.x * g.lanes) {
-      const size_t off = ((size_t)b * a.HW + p) * a.C + c0;
-      float d[8], av[8];
-      if (a.dpre) load8(a.dpre + off, d);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = gp[j];
-        if (a.out) {
-          float o[8];
-          load8(a.out + off, o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : d[j] * a.slope_out;
+      for (int u = 0; u < kU; ++u) {
+        const int p = p0 + u * g.lanes;
+        if (p < a.HW) {
+          const size_t off = ((size_t)b * a.HW + p) * C + c0;
+          if (a.dpre) dr[u] = ldg16(a.dpre + off);
+          else if (a.out) dr[u] = ldg16(a.out + off);
+          ar[u] = ldg16(a.a + off);
         }
       }
-      load8(a.a + off, av);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (av[j] - mean[j]) * rstd[j];
-        float z = k0[j] * (d[j] * gm[j] - s1[j] - xh * s2[j]);
-        if (av[j] <= 0.f) z *= a.slope_a;
-        d[j] = z;
-      }
-      store8(a.dz + off, d);
-      if (a.dbias) {
+      for (int u = 0; u < kU; ++u) {
+        const int p = p0 + u * g.lanes;
+        if (p >= a.HW) continue;
+        const size_t off = ((size_t)b * a.HW + p) * C + c0;
+        float d[8], av[8], t0[8], t1[8];
+        if (a.dpre) unpack8(dr[u], d);
+        else {
+          lds8(sP + 6 * C + c0, d);
+          if (a.out) {
+            unpack8(dr[u], t0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[0][j] += rbf(d[j]);
+            for (int j = 0; j < 8; ++j) d[j] = t0[j] > 0.f ? d[j] : d[j] * a.slope_out;
+          }
+        }
+        unpack8(ar[u], av);
+        lds8(sP + 2 * C + c0, t0);
+        lds8(sP + 3 * C + c0, t1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = d[j] * t0[j] - t1[j];      // g - S1/n
+        lds8(sP + c0, t0);
+        lds8(sP + C + c0, t1);
+        float xh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xh[j] = (av[j] - t0[j]) * t1[j];
+        lds8(sP + 4 * C + c0, t0);
+        lds8(sP + 5 * C + c0, t1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float z = t1[j] * (d[j] - xh[j] * t0[j]);
+          if (av[j] <= 0.f) z *= a.slope_a;
+          d[j] = z;
+        }
+        store8(a.dz + off, d);
+        if (a.dbias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[0][j] += rbf(d[j]);
+        }
       }
     }
   }
   if (a.dbias) {
     float* const dst[1] = {a.dbias};
-    block_channel_reduce<1>(acc, smem, a.C, lane_px, cgi, active, dst);
+    block_channel_reduce<1>(acc, sRed, C, lane_px, cgi, active, dst);
   }
 }
 
@@ -312,11 +417,16 @@ __global__ void __launch_bounds__(kEThreads) blk_bwd_apply_kernel(const BlkBwdAp
 // One warp per (image b, query slot i < nq, head). Query slot i < nc-1 is token 32*i (row 0 of chunk i); slots
 // nc-1 .. nc+30 are the 32 tokens of the last chunk. Output row i of att_small is what the reference leaves at
 // position i of `out` before proj (lunar_evaluator.py:203-216). Lane j owns key j of the chunk.
+template <int HD>
 __global__ void __launch_bounds__(256) attn_ref_rows_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ att,
                                                              int B, int N, int C, int heads, int nq_pad,
                                                              unsigned long long seed, unsigned int thresh16,
                                                              float drop_scale) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  constexpr int NCH = HD / 8;                 // 16-byte chunks per head row
+  constexpr int DPL = HD >= 32 ? HD / 32 : 1; // output dims per lane
+  __shared__ uint4 sv[8][32][NCH];            // per-warp V chunk, chunk index swizzled by the row
+  const int wib = threadIdx.x >> 5;
+  const int warp = blockIdx.x * 8 + wib;
   const int lane = threadIdx.x & 31;
   const int nc = N / 32;
   const int nq = nc + 31;
@@ -325,27 +435,37 @@ __global__ void __launch_bounds__(256) attn_ref_rows_kernel(const bf16* __restri
   const int h = warp % heads;
   const int i = (warp / heads) % nq;
   const int b = warp / (heads * nq);
-  const int hd = C / heads;
   const int chunk = i < nc - 1 ? i : nc - 1;
   const int qtok = i < nc - 1 ? 32 * i : 32 * (nc - 1) + (i - (nc - 1));
   const size_t row = (size_t)3 * C;
-  const bf16* qp = qkv + ((size_t)b * N + qtok) * row + h * hd;
-  const bf16* kp = qkv + ((size_t)b * N + 32 * chunk + lane) * row + C + h * hd;
-  const bf16* vbase = qkv + ((size_t)b * N + 32 * chunk) * row + 2 * C + h * hd;
-  float s = 0.f;
-  for (int d = 0; d < hd; d += 8) {
-    float qv[8], kv[8];
-    load8(qp + d, qv);
-    load8(kp + d, kv);
+  const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + qtok) * row + h * HD);
+  const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + 32 * chunk + lane) * row + C + h * HD);
+  const uint4* vp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + 32 * chunk + lane) * row + 2 * C + h * HD);
+  uint4 qr[NCH], kr[NCH], vr[NCH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += qv[j] * kv[j];
+  for (int c = 0; c < NCH; ++c) {
+    qr[c] = __ldg(qp + c);
+    kr[c] = __ldg(kp + c);
+    vr[c] = __ldg(vp + c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qr[c]);
+    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[c]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __bfloat1622float2(q2[j]), bb = __bfloat1622float2(k2[j]);
+      s += a.x * bb.x + a.y * bb.y;
+    }
+    sv[wib][lane][c ^ (lane & (NCH - 1))] = vr[c];
   }
   // reference dtype flow under bf16 autocast: scores and the scale product are bf16, softmax is fp32
-  s = rbf(rbf(s) * rbf(rsqrtf((float)hd)));
+  s = rbf(rbf(s) * rbf(rsqrtf((float)HD)));
   float m = s;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float e = __expf(s - m);
+  const float e = __expf(s - m);
   const float sum = warp_sum(e);
   float p = e / sum;
   if (thresh16) {
@@ -353,18 +473,25 @@ __global__ void __launch_bounds__(256) attn_ref_rows_kernel(const bf16* __restri
     p = drop_keep1(seed, idx, thresh16) ? p * drop_scale : 0.f;
   }
   p = rbf(p);
-  for (int d0 = 0; d0 < hd; d0 += 32) {
-    const int d = d0 + lane;
-    float o = 0.f;
-    if (d < hd) {
-      for (int j = 0; j < 32; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, p, j);
-        o += pj * __bfloat162float(vbase[(size_t)j * row + d]);
-      }
-      att[((size_t)b * nq_pad + i) * C + h * hd + d] = __float2bfloat16_rn(o);
-    } else {
-      for (int j = 0; j < 32; ++j) __shfl_sync(0xffffffffu, p, j);
+  __syncwarp();
+  const int d0 = lane * DPL;
+  float o[DPL];
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) o[k] = 0.f;
+  const bool active = d0 < HD;
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, p, j);
+    if (active) {
+      const bf16* vrow = reinterpret_cast<const bf16*>(&sv[wib][j][(d0 >> 3) ^ (j & (NCH - 1))]) + (d0 & 7);
+#pragma unroll
+      for (int k = 0; k < DPL; ++k) o[k] += pj * __bfloat162float(vrow[k]);
     }
+  }
+  if (active) {
+    bf16* dst = att + ((size_t)b * nq_pad + i) * C + h * HD + d0;
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) dst[k] = __float2bfloat16_rn(o[k]);
   }
 }
 
@@ -413,19 +540,29 @@ __global__ void __launch_bounds__(kEThreads) proj_bwd_gather_kernel(const bf16* 
   const int b = blockIdx.y, c0 = cgi * 8;
   float acc[1][8] = {};
   if (active) {
-    for (int p = blockIdx.x * g.lanes + lane_px; p < HW; p += gridDim.x * g.lanes) {
-      const size_t off = ((size_t)b * HW + p) * C + c0;
-      float v[8];
-      load8(dh2 + off, v);
-      if (thresh16) {
-        bool keep[8];
-        drop_keep8(seed, off >> 3, thresh16, keep);
+    for (int p0 = blockIdx.x * g.lanes * kU + lane_px; p0 < HW; p0 += gridDim.x * g.lanes * kU) {
+      float vv[kU][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = keep[j] ? rbf(v[j] * drop_scale) : 0.f;
+      for (int u = 0; u < kU; ++u) {
+        const int p = p0 + u * g.lanes;
+        if (p < HW) load8(dh2 + ((size_t)b * HW + p) * C + c0, vv[u]);
       }
-      if (p < nq) store8(dpo_small + ((size_t)b * nq_pad + p) * C + c0, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+      for (int u = 0; u < kU; ++u) {
+        const int p = p0 + u * g.lanes;
+        if (p >= HW) continue;
+        const size_t off = ((size_t)b * HW + p) * C + c0;
+        float (&v)[8] = vv[u];
+        if (thresh16) {
+          bool keep[8];
+          drop_keep8(seed, off >> 3, thresh16, keep);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = keep[j] ? rbf(v[j] * drop_scale) : 0.f;
+        }
+        if (p < nq) store8(dpo_small + ((size_t)b * nq_pad + p) * C + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+      }
     }
   }
   float* const dst[1] = {dbias};
@@ -433,10 +570,10 @@ __global__ void __launch_bounds__(kEThreads) proj_bwd_gather_kernel(const bf16* 
 }
 
 static int elem_blocks_per_image(int HW, int C, int B) {
-  const int lanes = kEThreads / (C / 8);
+  const int lanes = kEThreads / (C / 8) * kU;
   int per = (HW + lanes - 1) / lanes;
-  // aim for ~8 blocks per SM overall
-  int want = (148 * 8 + B - 1) / B;
+  // many more blocks than resident slots so the tail wave is a small fraction of the work
+  int want = (148 * 32 + B - 1) / B;
   if (want < 1) want = 1;
   return per < want ? per : want;
 }
@@ -451,7 +588,7 @@ extern "C" {
 int lun_channel_stats_bf16(const void* x, long P, int C, float* stats, void* stream) {
   if (!chan_ok(C)) return LUN_E_SHAPE;
   const int lanes = kEThreads / (C / 8);
-  long blocks = (P + lanes - 1) / lanes;
+  long blocks = (P + lanes * kU - 1) / (lanes * kU);
   if (blocks > 148 * 8) blocks = 148 * 8;
   channel_stats_kernel<<<(int)blocks, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)x, stats, P, C);
@@ -481,7 +618,7 @@ int lun_affine_fwd_bf16(const void* x, const float* scale, const float* shift, c
   a.B = B; a.HW = HW; a.C = C; a.slope = slope;
   const int lanes = kEThreads / (C / 8);
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
-  affine_fwd_kernel<<<grid, kEThreads, pool ? lanes * C * sizeof(float) : 0, (cudaStream_t)stream>>>(a);
+  affine_fwd_kernel<<<grid, kEThreads, (6 * C + (pool ? lanes * C : 0)) * sizeof(float), (cudaStream_t)stream>>>(a);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
@@ -496,7 +633,7 @@ int lun_block_bwd_reduce_bf16(const void* dout, const float* gpool, const void* 
   a.slope_out = slope_out;
   const int lanes = kEThreads / (C / 8);
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
-  blk_bwd_reduce_kernel<<<grid, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(a);
+  blk_bwd_reduce_kernel<<<grid, kEThreads, (4 * C + lanes * 2 * C) * sizeof(float), (cudaStream_t)stream>>>(a);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
@@ -513,7 +650,7 @@ int lun_block_bwd_apply_bf16(const void* dpre, const float* gpool, const void* o
   a.inv_n = 1.f / ((float)B * (float)HW);
   const int lanes = kEThreads / (C / 8);
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
-  blk_bwd_apply_kernel<<<grid, kEThreads, dbias ? lanes * C * sizeof(float) : 0, (cudaStream_t)stream>>>(a);
+  blk_bwd_apply_kernel<<<grid, kEThreads, (7 * C + (dbias ? lanes * C : 0)) * sizeof(float), (cudaStream_t)stream>>>(a);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
@@ -526,8 +663,18 @@ int lun_attn_ref_rows_bf16(const void* qkv, void* att_small, int B, int N, int C
   const long warps = (long)B * nq * heads;
   const unsigned int th = drop_p > 0.f ? (unsigned int)(drop_p * 65536.f + 0.5f) : 0u;
   const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  attn_ref_rows_kernel<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)qkv, (bf16*)att_small, B, N, C, heads, nq_pad, seed, th, ds);
+  const int hd = C / heads;
+  const int blocks = (int)((warps + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LUN_ATTN(HD_)                                                                                              \
+  attn_ref_rows_kernel<HD_><<<blocks, 256, 0, st>>>((const bf16*)qkv, (bf16*)att_small, B, N, C, heads, nq_pad, seed, \
+                                                     th, ds)
+  if (hd == 64) LUN_ATTN(64);
+  else if (hd == 32) LUN_ATTN(32);
+  else if (hd == 16) LUN_ATTN(16);
+  else if (hd == 8) LUN_ATTN(8);
+  else return LUN_E_SHAPE;
+#undef LUN_ATTN
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
