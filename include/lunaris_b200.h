@@ -100,6 +100,15 @@ int lun_block_bwd_apply_bf16(const void* dpre, const float* gpool, const void* o
 int lun_attn_ref_rows_bf16(const void* qkv, void* att_small, int B, int N, int C, int heads, int nq_pad,
                            unsigned long long seed, float drop_p, void* stream);
 
+/* Same attention with the dead work removed: only the N/32+31 query rows that survive the scatter are projected
+ * (q_small [B, nq_pad, C], rows gathered by lun_gather_query_rows_bf16 then multiplied by Wq), K and V come from a
+ * [B, N, 2C] tensor (channel blocks K | V). Results are identical to lun_attn_ref_rows_bf16 on the full qkv. */
+int lun_attn_ref_rows_split_bf16(const void* q_small, const void* kv, void* att_small, int B, int N, int C, int heads,
+                                 int nq_pad, unsigned long long seed, float drop_p, void* stream);
+/* out[b, i, :] = x[b, qtok(i), :] for the query tokens the as-executed attention uses: qtok(i) = 32 i for
+ * i < N/32 - 1, else the 32 tokens of the last chunk (lunar_evaluator.py:203-216). */
+int lun_gather_query_rows_bf16(const void* x, void* out, int B, int N, int C, int nq_pad, void* stream);
+
 /* y[b,p,:] = proj_drop( p < nq ? proj_small[b,p,:] : bias )  (lunar_evaluator.py:224-225 on the mostly-zero input). */
 int lun_proj_expand_bf16(const void* proj_small, const float* bias, void* y, int B, int HW, int C, int nq, int nq_pad,
                          unsigned long long seed, float drop_p, void* stream);

@@ -417,82 +417,100 @@ __global__ void __launch_bounds__(kEThreads, 3) blk_bwd_apply_kernel(const BlkBw
 // One warp per (image b, query slot i < nq, head). Query slot i < nc-1 is token 32*i (row 0 of chunk i); slots
 // nc-1 .. nc+30 are the 32 tokens of the last chunk. Output row i of att_small is what the reference leaves at
 // position i of `out` before proj (lunar_evaluator.py:203-216). Lane j owns key j of the chunk.
+// Loads are laid out so that HD/8 adjacent lanes read one 128-byte (or shorter) head row: every LDG.128 of the warp
+// touches whole cache lines (the earlier one-row-per-lane layout was L1-tag bound: 32 lines per instruction).
+//   q: [B, nq_pad, C] rows already gathered/projected (q_stride = C) or the full qkv tensor (q_stride = 3C)
+//   k, v: base pointers of the K and V channel blocks, row stride kv_stride elements
 template <int HD>
-__global__ void __launch_bounds__(256) attn_ref_rows_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ att,
-                                                             int B, int N, int C, int heads, int nq_pad,
-                                                             unsigned long long seed, unsigned int thresh16,
-                                                             float drop_scale) {
-  constexpr int NCH = HD / 8;                 // 16-byte chunks per head row
-  constexpr int DPL = HD >= 32 ? HD / 32 : 1; // output dims per lane
-  __shared__ uint4 sv[8][32][NCH];            // per-warp V chunk, chunk index swizzled by the row
-  const int wib = threadIdx.x >> 5;
-  const int warp = blockIdx.x * 8 + wib;
+__global__ void __launch_bounds__(256) attn_ref_rows_kernel(const bf16* __restrict__ q, long q_img_stride,
+                                                             int q_stride, int q_is_token_indexed,
+                                                             const bf16* __restrict__ k, const bf16* __restrict__ v,
+                                                             int kv_stride, bf16* __restrict__ att, int B, int N,
+                                                             int C, int heads, int nq_pad, unsigned long long seed,
+                                                             unsigned int thresh16, float drop_scale) {
+  constexpr int LPR = HD / 8;        // lanes per row (16-byte chunks per head row)
+  constexpr int RPI = 32 / LPR;      // rows per load instruction
+  constexpr int NT = 32 / RPI;       // load instructions per 32-row chunk (== LPR)
+  const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int nc = N / 32;
   const int nq = nc + 31;
-  const int total = B * nq * heads;
-  if (warp >= total) return;
+  if (warp >= B * nq * heads) return;
   const int h = warp % heads;
   const int i = (warp / heads) % nq;
   const int b = warp / (heads * nq);
   const int chunk = i < nc - 1 ? i : nc - 1;
   const int qtok = i < nc - 1 ? 32 * i : 32 * (nc - 1) + (i - (nc - 1));
-  const size_t row = (size_t)3 * C;
-  const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + qtok) * row + h * HD);
-  const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + 32 * chunk + lane) * row + C + h * HD);
-  const uint4* vp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + 32 * chunk + lane) * row + 2 * C + h * HD);
-  uint4 qr[NCH], kr[NCH], vr[NCH];
+  const int c8 = lane % LPR, rg = lane / LPR;
+  const long qrow = q_is_token_indexed ? qtok : i;
+  const uint4 qv = __ldg(reinterpret_cast<const uint4*>(q + b * q_img_stride + qrow * q_stride + h * HD + c8 * 8));
+  uint4 kr[NT], vr[NT];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    qr[c] = __ldg(qp + c);
-    kr[c] = __ldg(kp + c);
-    vr[c] = __ldg(vp + c);
+  for (int t = 0; t < NT; ++t) {
+    const size_t roff = ((size_t)b * N + 32 * chunk + t * RPI + rg) * kv_stride + h * HD + c8 * 8;
+    kr[t] = __ldg(reinterpret_cast<const uint4*>(k + roff));
+    vr[t] = __ldg(reinterpret_cast<const uint4*>(v + roff));
   }
-  float s = 0.f;
+  float qf[8];
+  unpack8(qv, qf);
+  const float scale = rbf(rsqrtf((float)HD));
+  float s[NT];
+  float m = -3.0e38f;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qr[c]);
-    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[c]);
+  for (int t = 0; t < NT; ++t) {
+    float kf[8];
+    unpack8(kr[t], kf);
+    float d = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 a = __bfloat1622float2(q2[j]), bb = __bfloat1622float2(k2[j]);
-      s += a.x * bb.x + a.y * bb.y;
+    for (int j = 0; j < 8; ++j) d += qf[j] * kf[j];
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    // reference dtype flow under bf16 autocast: scores and the scale product are bf16, softmax is fp32
+    s[t] = rbf(rbf(d) * scale);
+    m = fmaxf(m, s[t]);
+  }
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    s[t] = __expf(s[t] - m);
+    sum += s[t];
+  }
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    float p = s[t] * inv;
+    if (thresh16) {
+      const unsigned long long idx = ((unsigned long long)warp << 5) + (t * RPI + rg);
+      p = drop_keep1(seed, idx, thresh16) ? p * drop_scale : 0.f;
     }
-    sv[wib][lane][c ^ (lane & (NCH - 1))] = vr[c];
-  }
-  // reference dtype flow under bf16 autocast: scores and the scale product are bf16, softmax is fp32
-  s = rbf(rbf(s) * rbf(rsqrtf((float)HD)));
-  float m = s;
+    p = rbf(p);
+    float vf[8];
+    unpack8(vr[t], vf);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  const float e = __expf(s - m);
-  const float sum = warp_sum(e);
-  float p = e / sum;
-  if (thresh16) {
-    const unsigned long long idx = ((unsigned long long)warp << 5) + lane;
-    p = drop_keep1(seed, idx, thresh16) ? p * drop_scale : 0.f;
+    for (int j = 0; j < 8; ++j) o8[j] += p * vf[j];
   }
-  p = rbf(p);
-  __syncwarp();
-  const int d0 = lane * DPL;
-  float o[DPL];
 #pragma unroll
-  for (int k = 0; k < DPL; ++k) o[k] = 0.f;
-  const bool active = d0 < HD;
-#pragma unroll 8
-  for (int j = 0; j < 32; ++j) {
-    const float pj = __shfl_sync(0xffffffffu, p, j);
-    if (active) {
-      const bf16* vrow = reinterpret_cast<const bf16*>(&sv[wib][j][(d0 >> 3) ^ (j & (NCH - 1))]) + (d0 & 7);
+  for (int o = LPR; o < 32; o <<= 1) {
 #pragma unroll
-      for (int k = 0; k < DPL; ++k) o[k] += pj * __bfloat162float(vrow[k]);
-    }
+    for (int j = 0; j < 8; ++j) o8[j] += __shfl_xor_sync(0xffffffffu, o8[j], o);
   }
-  if (active) {
-    bf16* dst = att + ((size_t)b * nq_pad + i) * C + h * HD + d0;
-#pragma unroll
-    for (int k = 0; k < DPL; ++k) dst[k] = __float2bfloat16_rn(o[k]);
-  }
+  if (rg == 0) store8(att + ((size_t)b * nq_pad + i) * C + h * HD + c8 * 8, o8);
+}
+
+// out[b, i, :] = x[b, qtok(i), :]: the N/32+31 query tokens the as-executed attention actually uses.
+__global__ void gather_query_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int C, int nq,
+                                         int nq_pad) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int nc = N / 32;
+  const int qtok = i < nc - 1 ? 32 * i : 32 * (nc - 1) + (i - (nc - 1));
+  const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * N + qtok) * C);
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * nq_pad + i) * C);
+  for (int c = threadIdx.x; c < C / 8; c += blockDim.x) dst[c] = __ldg(src + c);
 }
 
 // h2[b,p,:] = dropout( p < nq ? proj_small[b,p,:] : bf16(bias) )   (lunar_evaluator.py:224-225)
@@ -655,8 +673,9 @@ int lun_block_bwd_apply_bf16(const void* dpre, const float* gpool, const void* o
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
-int lun_attn_ref_rows_bf16(const void* qkv, void* att_small, int B, int N, int C, int heads, int nq_pad,
-                           unsigned long long seed, float drop_p, void* stream) {
+static int launch_attn(const bf16* q, long q_img_stride, int q_stride, int q_tok, const bf16* k, const bf16* v,
+                       int kv_stride, bf16* att, int B, int N, int C, int heads, int nq_pad, unsigned long long seed,
+                       float drop_p, cudaStream_t st) {
   if (N % 32 || C % heads || (C / heads) % 8) return LUN_E_SHAPE;
   const int nq = N / 32 + 31;
   if (nq_pad < nq) return LUN_E_SHAPE;
@@ -665,16 +684,40 @@ int lun_attn_ref_rows_bf16(const void* qkv, void* att_small, int B, int N, int C
   const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int hd = C / heads;
   const int blocks = (int)((warps + 7) / 8);
-  cudaStream_t st = (cudaStream_t)stream;
-#define LUN_ATTN(HD_)                                                                                              \
-  attn_ref_rows_kernel<HD_><<<blocks, 256, 0, st>>>((const bf16*)qkv, (bf16*)att_small, B, N, C, heads, nq_pad, seed, \
-                                                     th, ds)
+#define LUN_ATTN(HD_)                                                                                             \
+  attn_ref_rows_kernel<HD_><<<blocks, 256, 0, st>>>(q, q_img_stride, q_stride, q_tok, k, v, kv_stride, att, B, N, C, \
+                                                     heads, nq_pad, seed, th, ds)
   if (hd == 64) LUN_ATTN(64);
   else if (hd == 32) LUN_ATTN(32);
   else if (hd == 16) LUN_ATTN(16);
   else if (hd == 8) LUN_ATTN(8);
+  else if (hd == 128) LUN_ATTN(128);
   else return LUN_E_SHAPE;
 #undef LUN_ATTN
+  lun::note_launch(1);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_attn_ref_rows_bf16(const void* qkv, void* att_small, int B, int N, int C, int heads, int nq_pad,
+                           unsigned long long seed, float drop_p, void* stream) {
+  const bf16* base = (const bf16*)qkv;
+  return launch_attn(base, (long)N * 3 * C, 3 * C, 1, base + C, base + 2 * C, 3 * C, (bf16*)att_small, B, N, C, heads,
+                     nq_pad, seed, drop_p, (cudaStream_t)stream);
+}
+
+int lun_attn_ref_rows_split_bf16(const void* q_small, const void* kv, void* att_small, int B, int N, int C, int heads,
+                                 int nq_pad, unsigned long long seed, float drop_p, void* stream) {
+  const bf16* kvb = (const bf16*)kv;
+  return launch_attn((const bf16*)q_small, (long)nq_pad * C, C, 0, kvb, kvb + C, 2 * C, (bf16*)att_small, B, N, C,
+                     heads, nq_pad, seed, drop_p, (cudaStream_t)stream);
+}
+
+int lun_gather_query_rows_bf16(const void* x, void* out, int B, int N, int C, int nq_pad, void* stream) {
+  if (N % 32 || C % 8) return LUN_E_SHAPE;
+  const int nq = N / 32 + 31;
+  if (nq_pad < nq) return LUN_E_SHAPE;
+  dim3 grid(nq, B);
+  gather_query_rows_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, N, C, nq, nq_pad);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }

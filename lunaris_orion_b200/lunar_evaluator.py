@@ -218,6 +218,13 @@ def _packed(param, kind):
         t = ops.pack_conv_weight_dgrad(param)
     elif kind == "f32":
         t = param.detach().float().contiguous()
+    elif kind in ("q_fwd", "kv_fwd"):            # qkv conv weight [3C, C, 1, 1] split into its Q and K|V row blocks
+        C = param.shape[1]
+        rows = param.detach()[:C] if kind == "q_fwd" else param.detach()[C:]
+        t = ops.pack_conv_weight(rows)
+    elif kind in ("q_f32", "kv_f32"):            # qkv bias [3C]
+        C = param.shape[0] // 3
+        t = (param.detach()[:C] if kind == "q_f32" else param.detach()[C:]).float().contiguous()
     else:
         raise KeyError(kind)
     _pack_cache[key] = (ver, t, param)
@@ -329,13 +336,20 @@ def _attention_forward(att, x1, B, H, W, training, save):
     p_attn = att.attn_drop.p if training else 0.0
     p_proj = att.proj_drop.p if training else 0.0
     att._touch_rel_pos(H, W, x1.device)
-    qkv = ops.conv2d_fprop(x1.view(B, H, W, C), _packed(att.qkv.weight, "fwd"), 1, 1, 0,
-                           bias=_packed(att.qkv.bias, "f32"))
+    # Only N/32+31 query rows survive the reference's chunk-index scatter: K and V are computed for every token, Q
+    # only for those rows (identical results, one third of the qkv FLOPs and output bytes removed).
+    kv = ops.conv2d_fprop(x1.view(B, H, W, C), _packed(att.qkv.weight, "kv_fwd"), 1, 1, 0,
+                          bias=_packed(att.qkv.bias, "kv_f32"))
+    xq = torch.zeros(B, nq_pad, C, device=x1.device, dtype=torch.bfloat16)
+    check(lib.lun_gather_query_rows_bf16(x1.data_ptr(), xq.data_ptr(), B, HW, C, nq_pad, _stream()),
+          "lun_gather_query_rows_bf16")
+    q_small = ops.linear_fprop(xq.view(B * nq_pad, C), _packed(att.qkv.weight, "q_fwd").view(C, C),
+                               _packed(att.qkv.bias, "q_f32"), out_f32=False)
     att_small = torch.zeros(B, nq_pad, C, device=x1.device, dtype=torch.bfloat16)
-    check(lib.lun_attn_ref_rows_bf16(qkv.data_ptr(), att_small.data_ptr(), B, HW, C, att.num_heads, nq_pad,
-                                     _cpu_seed() if p_attn > 0 else 0, float(p_attn), _stream()),
-          "lun_attn_ref_rows_bf16")
-    del qkv
+    check(lib.lun_attn_ref_rows_split_bf16(q_small.data_ptr(), kv.data_ptr(), att_small.data_ptr(), B, HW, C,
+                                           att.num_heads, nq_pad, _cpu_seed() if p_attn > 0 else 0, float(p_attn),
+                                           _stream()), "lun_attn_ref_rows_split_bf16")
+    del kv
     wp = _packed(att.proj.weight, "fwd")
     proj_small = ops.linear_fprop(att_small.view(B * nq_pad, C), wp.view(C, C), _packed(att.proj.bias, "f32"),
                                   out_f32=False)

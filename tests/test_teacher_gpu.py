@@ -82,3 +82,36 @@ def test_dropout_kernels_statistics_and_replay(cuda_dev):
     torch.cuda.synchronize()
     assert torch.equal(dpo[:, :nq].float(), yf[:, :nq])                       # same mask as the forward
     assert torch.allclose(db, yf.sum((0, 1)), rtol=1e-3)
+
+
+@pytest.mark.gpu
+def test_attention_rows_split_equals_full_qkv_and_oracle(cuda_dev):
+    """The pruned attention (Q rows gathered, K|V tensor) equals the kernel on the full qkv tensor bit-for-bit and
+    matches the oracle's as-executed scatter (local_attention, lunar_evaluator.py:203-216)."""
+    import ctypes
+    from lunaris_orion_b200 import _capi
+    from oracle import restatement as R
+    lib = _capi.lib()
+    B, H, C, heads = 2, 64, 128, 8
+    N = H * H
+    nq = N // 32 + 31
+    nq_pad = (nq + 7) // 8 * 8
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B, N, 3 * C, generator=g).to(torch.bfloat16).to(cuda_dev)
+    s = torch.cuda.current_stream().cuda_stream
+    full = torch.zeros(B, nq_pad, C, device=cuda_dev, dtype=torch.bfloat16)
+    _capi.check(lib.lun_attn_ref_rows_bf16(qkv.data_ptr(), full.data_ptr(), B, N, C, heads, nq_pad, 0,
+                                           ctypes.c_float(0.0), s), "attn")
+    qg = torch.zeros(B, nq_pad, 3 * C, device=cuda_dev, dtype=torch.bfloat16)
+    _capi.check(lib.lun_gather_query_rows_bf16(qkv.data_ptr(), qg.data_ptr(), B, N, 3 * C, nq_pad, s), "gather")
+    q_small = qg[:, :, :C].contiguous()
+    kv = qkv[:, :, C:].contiguous()
+    split = torch.zeros(B, nq_pad, C, device=cuda_dev, dtype=torch.bfloat16)
+    _capi.check(lib.lun_attn_ref_rows_split_bf16(q_small.data_ptr(), kv.data_ptr(), split.data_ptr(), B, N, C, heads,
+                                                 nq_pad, 0, ctypes.c_float(0.0), s), "attn split")
+    torch.cuda.synchronize()
+    assert torch.equal(full, split)
+    ref = R.local_attention(qkv.float().cpu().view(B, H, H, 3 * C).permute(0, 3, 1, 2), "reference")
+    ref = ref.permute(0, 2, 3, 1).reshape(B, N, C)
+    assert ref[:, nq:].abs().max().item() == 0.0                       # everything past row nq stays zero
+    assert tc.rel_err(full[:, :nq], ref[:, :nq]) < 2e-2
