@@ -85,29 +85,30 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_blk = tile % n_blocks;
-        int m = tile / n_blocks;
-        const int tw = m % g.ntw;
-        m /= g.ntw;
-        const int th = m % g.nth;
-        const int tb = m / g.nth;
-        const int w0 = tw * g.TW * g.in_mul, h0 = th * g.TH * g.in_mul, b0 = tb * g.TB;
-        for (int t = 0; t < g.ntaps; ++t) {
-          const int cw = w0 + g.dx[t], ch = h0 + g.dy[t];
-          const int wrow = g.slab[t] * g.Cout + n_blk * block_n;
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&bars->empty[s], ph ^ 1);
-            uint8_t* sa = smem + s * stage_bytes;
+    // ------------------------------------------------------------ TMA producer (lane 0: A tile, lane 1: B tile)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % n_blocks;
+      int m = tile / n_blocks;
+      const int tw = m % g.ntw;
+      m /= g.ntw;
+      const int th = m % g.nth;
+      const int tb = m / g.nth;
+      const int w0 = tw * g.TW * g.in_mul, h0 = th * g.TH * g.in_mul, b0 = tb * g.TB;
+      for (int t = 0; t < g.ntaps; ++t) {
+        const int cw = w0 + g.dx[t], ch = h0 + g.dy[t];
+        const int wrow = g.slab[t] * g.Cout + n_blk * block_n;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&bars->empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          if (lane == 0) {
             mbar_expect_tx(&bars->full[s], stage_bytes);
             tma_load_4d(sa, &tmA, &bars->full[s], kc * 64, cw, ch, b0);
+          } else if (lane == 1) {
             tma_load_2d(sa + kABytes, &tmB, &bars->full[s], kc * 64, wrow);
-            if (++s == stages) { s = 0; ph ^= 1; }
           }
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
     }

@@ -85,32 +85,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   auto chunk_lo = [&](int split) { return static_cast<int>(static_cast<long long>(chunks) * split / g.splits); };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int split = u / tiles;
-        int t = u % tiles;
-        const int m_blk = t % m_blocks;
-        t /= m_blocks;
-        const int n_blk = t % n_blocks;
-        const int tap = t / n_blocks;
-        const int c_lo = chunk_lo(split), c_hi = chunk_lo(split + 1);
-        for (int c = c_lo; c < c_hi; ++c) {
-          const int tw = c % g.ntw;
-          const int th = (c / g.ntw) % g.nth;
-          const int tb = c / (g.ntw * g.nth);
-          mbar_wait(&bars->empty[s], ph ^ 1);
-          uint8_t* sa = smem + s * stage_bytes;
-          mbar_expect_tx(&bars->full[s], stage_bytes);
+    // TMA producer: the whole warp walks the ring; lane 0 arms the barrier, lanes 0..nbox-1 each issue one box so
+    // the 2 + block_n/64 loads of a stage are issued in parallel instead of back to back by one thread.
+    const int nbox = 2 + block_n / 64;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int split = u / tiles;
+      int t = u % tiles;
+      const int m_blk = t % m_blocks;
+      t /= m_blocks;
+      const int n_blk = t % n_blocks;
+      const int tap = t / n_blocks;
+      const int c_lo = chunk_lo(split), c_hi = chunk_lo(split + 1);
+      // chunk -> (tb, th, tw) once per unit, then incremental (no integer divisions inside the ring loop)
+      int tw = c_lo % g.ntw, th = (c_lo / g.ntw) % g.nth, tb = c_lo / (g.ntw * g.nth);
+      for (int c = c_lo; c < c_hi; ++c) {
+        mbar_wait(&bars->empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * stage_bytes;
+        if (lane == 0) mbar_expect_tx(&bars->full[s], stage_bytes);
+        __syncwarp();
+        if (lane < 2) {
           const int yw = tw * g.TW * g.dy_mul + g.dy_pw, yh = th * g.TH * g.dy_mul + g.dy_ph;
-          tma_load_4d(sa, &tmDY, &bars->full[s], m_blk * 128, yw, yh, tb * g.TB);
-          tma_load_4d(sa + 8192, &tmDY, &bars->full[s], m_blk * 128 + 64, yw, yh, tb * g.TB);
+          tma_load_4d(sa + lane * 8192, &tmDY, &bars->full[s], m_blk * 128 + lane * 64, yw, yh, tb * g.TB);
+        } else if (lane < nbox) {
+          const int j = lane - 2;
           const int xw = tw * g.TW * g.in_mul + g.dx[tap], xh = th * g.TH * g.in_mul + g.dy[tap];
-          for (int j = 0; j < block_n / 64; ++j)
-            tma_load_4d(sa + kWgABytes + j * 8192, &tmX, &bars->full[s], n_blk * block_n + j * 64, xw, xh,
-                        tb * g.TB);
-          if (++s == stages) { s = 0; ph ^= 1; }
+          tma_load_4d(sa + kWgABytes + j * 8192, &tmX, &bars->full[s], n_blk * block_n + j * 64, xw, xh, tb * g.TB);
+        }
+        if (++s == stages) { s = 0; ph ^= 1; }
+        if (++tw == g.ntw) {
+          tw = 0;
+          if (++th == g.nth) { th = 0; ++tb; }
         }
       }
     }
@@ -231,8 +237,13 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
   const int m_blocks = (g.Cout + 127) / 128, n_blocks = (g.Cin + bn - 1) / bn;
   const int tiles = m_blocks * n_blocks * g.ntaps;
   const int chunks = g.ntb * g.nth * g.ntw;
-  // enough K-splits for ~4 units per SM, but keep at least 8 k-chunks per unit
-  int splits = (4 * num_sms() + tiles - 1) / tiles;
+  // K-splits: make the unit count a multiple of the SM count when the reduction is long enough (perfect balance of
+  // the persistent grid), otherwise ~4 units per SM; keep at least 8 k-chunks per unit
+  int a = tiles, b = num_sms();
+  while (b) { const int r = a % b; a = b; b = r; }
+  int splits = num_sms() / a;                       // tiles * splits == lcm(tiles, SMs)
+  while (splits * tiles < 4 * num_sms()) splits *= 2;
+  if (splits > chunks / 8) splits = (4 * num_sms() + tiles - 1) / tiles;
   if (splits > chunks / 8) splits = chunks / 8;
   if (splits < 1) splits = 1;
   g.splits = splits;
