@@ -19,7 +19,7 @@
 
 namespace lun {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
 struct __align__(16) PipeBars {
@@ -41,7 +41,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int b_bytes = block_n * 128;
   const int stage_bytes = kABytes + b_bytes;
   const int stages = g.stages;
-  uint8_t* s_stage = smem + stages * stage_bytes;  // 16 KB output staging tile (128 rows x 128 B, swizzled)
+  uint8_t* s_stage = smem + stages * stage_bytes;  // 2 x 8 KB output staging tiles (128 rows x 64 B, 64B swizzle)
   PipeBars* bars = reinterpret_cast<PipeBars*>(s_stage + kABytes);
   float* s_bias = reinterpret_cast<float*>(bars + 1);   // [Cout]
   float* s_stats = s_bias + g.Cout;                     // [2 * Cout] when EPI_STATS
@@ -67,7 +67,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tfull[i], 1);
-      mbar_init(&bars->tempty[i], 4);
+      mbar_init(&bars->tempty[i], 8);
     }
     fence_barrier_init();
   }
@@ -144,13 +144,23 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps share each TMEM lane quarter and split the accumulator columns (half 0: first chunks, half 1: the
+    // rest), so a 128x256 tile is drained by 8 warps; each half owns an 8 KB staging tile (128 rows x 32 channels,
+    // 64-byte swizzle) that leaves through its own TMA store. TMEM loads are software-pipelined one chunk ahead.
+    const int ew = warp - 2;
     const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = ew >> 2;
     const int row = q * 32 + lane;      // accumulator row == pixel index inside the tile
     const bool do_stats = g.flags & EPI_STATS, out_f32 = g.flags & EPI_OUT_F32, tma_out = g.flags & EPI_TMA_STORE;
     const float slope = (g.flags & EPI_LEAKY) ? g.slope : 1.f;
-    const bool epi_leader = threadIdx.x == 64;
-    const uint32_t stg_row = smem_u32(s_stage) + row * 128;
+    const bool half_leader = (threadIdx.x == 64 + half * 128);
+    const uint32_t stg_base = smem_u32(s_stage) + half * 8192;
+    const uint32_t stg_row = stg_base + row * 64;
+    const int nchunks = block_n >> 5;
+    const int ch_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
+    const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
+    const int bar_a = 1 + 2 * half, bar_b = 2 + 2 * half;
     int acc = 0;
     uint32_t pacc = 0;
     bool store_pending = false;
@@ -170,22 +180,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&bars->tfull[acc], pacc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * block_n;
-      for (int c0 = 0; c0 < block_n; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
+      // process one 32-column chunk held in registers `r` (bias, activation, store, statistics)
+      auto process = [&](uint32_t (&r)[32], int ch) {
+        const int c0 = ch << 5;
         const int nb = n_blk * block_n + c0;
         float bv[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 t = *reinterpret_cast<const float4*>(s_bias + nb + 4 * j);
           bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
-        }
-        tmem_ld_wait();
-        if (c0 + 32 >= block_n) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->tempty[acc]);
         }
         float v[32];
 #pragma unroll
@@ -204,34 +207,29 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           if (tma_out) {
-            const int half = (c0 >> 5) & 1;
-            if (half == 0) {
-              // the staging tile is reused: wait until the previous TMA store has finished reading it
-              if (store_pending) {
-                if (epi_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-              }
+            // the staging tile is reused: wait until the previous TMA store has finished reading it
+            if (store_pending) {
+              if (half_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t chunk = static_cast<uint32_t>((half * 4 + j) ^ (row & 7));
+              const uint32_t chunk = static_cast<uint32_t>(j ^ ((row >> 1) & 3));
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + (chunk << 4)), "r"(p[4 * j]),
                            "r"(p[4 * j + 1]), "r"(p[4 * j + 2]), "r"(p[4 * j + 3])
                            : "memory");
             }
-            if (half == 1) {
-              fence_proxy_async();
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              if (epi_leader) {
-                asm volatile(
-                    "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                        &tmO),
-                    "r"(smem_u32(s_stage)), "r"(g.o_coff + nb - 32), "r"(tw * g.TW), "r"(th * g.TH), "r"(tb * g.TB)
-                    : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
-              store_pending = true;
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");
+            if (half_leader) {
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                      &tmO),
+                  "r"(stg_base), "r"(g.o_coff + nb), "r"(tw * g.TW), "r"(th * g.TH), "r"(tb * g.TB)
+                  : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            store_pending = true;
           } else if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + obase + c0);
 #pragma unroll
@@ -270,13 +268,29 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           atomicAdd(&s_stats[nb + lane], s1[0]);
           atomicAdd(&s_stats[g.Cout + nb + lane], s2[0]);
         }
+      };
+      uint32_t ra[32], rb[32];
+      if (ch_lo < ch_hi) tmem_ld32(taddr + ch_lo * 32, ra);
+      for (int ch = ch_lo; ch < ch_hi; ch += 2) {
+        tmem_ld_wait();                                               // ra has landed
+        if (ch + 1 < ch_hi) tmem_ld32(taddr + (ch + 1) * 32, rb);     // prefetch while ra is processed
+        process(ra, ch);
+        if (ch + 1 < ch_hi) {
+          tmem_ld_wait();                                             // rb has landed
+          if (ch + 2 < ch_hi) tmem_ld32(taddr + (ch + 2) * 32, ra);
+          process(rb, ch + 1);
+        }
       }
+      // every TMEM read of this accumulator stage by this warp has completed (tmem_ld_wait above)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tempty[acc]);
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
-    if (store_pending && epi_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (store_pending && half_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < 2 * g.Cout; i += 128) atomicAdd(stats + i, s_stats[i]);
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < 2 * g.Cout; i += 256) atomicAdd(stats + i, s_stats[i]);
     }
   }
 
@@ -307,18 +321,22 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 // 4-D bf16 NHWC activation map {C, W, H, B}; box = {64, bw, bh, bb} elements traversed with strides {1, es, es, 1}.
-int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b,
-                   int estride) {
+static int make_tmap_nhwc_ex(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_c, int box_w,
+                            int box_h, int box_b, int estride, CUtensorMapSwizzle swz) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return 101;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
   cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 102;
+}
+int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b,
+                   int estride) {
+  return make_tmap_nhwc_ex(m, base, B, H, W, C, 64, box_w, box_h, box_b, estride, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // 2-D bf16 row-major matrix map {cols, rows}; box = {64, box_rows}.
@@ -372,7 +390,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
 
   CUtensorMap tmA, tmB, tmO;
   // coalesced asynchronous output path: bf16, dense pixel mapping, 64-channel boxes
-  if (!(g.flags & EPI_OUT_F32) && g.o_mul == 1 && g.block_n % 64 == 0)
+  if (!(g.flags & EPI_OUT_F32) && g.o_mul == 1)
     g.flags |= EPI_TMA_STORE;
   else
     g.flags &= ~EPI_TMA_STORE;
@@ -382,7 +400,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   if (rc) return rc;
 
   if (g.flags & EPI_TMA_STORE) {
-    rc = make_tmap_nhwc(&tmO, out, g.GB, g.OH, g.OW, g.ldo, g.TW, g.TH, g.TB, 1);
+    rc = make_tmap_nhwc_ex(&tmO, out, g.GB, g.OH, g.OW, g.ldo, 32, g.TW, g.TH, g.TB, 1, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   } else {
     tmO = tmA;
