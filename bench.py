@@ -87,6 +87,7 @@ def run_ours(a):
     import torch.distributed as dist
     from lunaris_orion_b200 import _capi, ops
     from lunaris_orion_b200.train_hybrid import TrainingManager
+    from lunaris_orion_b200.lunar_generate import sprites_to_tensor
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -127,8 +128,7 @@ def run_ours(a):
     host_metrics = torch.empty(12, dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
-        u8 = host_u8[i % 4].to(dev, non_blocking=True)
-        x = u8.permute(0, 3, 1, 2).float().div_(127.5).sub_(1.0)
+        x = sprites_to_tensor(host_u8[i % 4].to(dev, non_blocking=True))
         m = tm._process_batch(x, i, return_tensor=True)
         host_metrics.copy_(m, non_blocking=True)
         torch.cuda.current_stream().synchronize()

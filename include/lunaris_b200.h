@@ -166,6 +166,19 @@ int lun_reparam_fwd(const float* mulv, const float* eps, void* z, int B, int L, 
 int lun_reparam_bwd(const float* mulv, const float* eps, const void* dz, const float* dmu, const float* dlogvar,
                     void* dmulv, int B, int L, void* stream);
 
+/* Step losses in one pass (train_hybrid.py:859-862): sums[0] += sum (recon-x)^2 over n_img elements,
+ * sums[1] += sum (1 + logvar - mu^2 - exp(logvar)) over B*L (caller zeroes sums; recon_loss = sums[0]/n_img,
+ * kl_loss = -0.5*sums[1]/(B*L)). mulv = [mu | logvar] packed [B, 2L]. The backward turns the two upstream scalar
+ * gradients g[0] (recon_loss), g[1] (kl_loss) (device memory) into d_recon and d_mulv. */
+int lun_vae_loss_fwd(const float* recon, const float* images, const float* mulv, float* sums, long n_img, int B, int L,
+                     void* stream);
+int lun_vae_loss_bwd(const float* recon, const float* images, const float* mulv, const float* g, float* drecon,
+                     float* dmulv, long n_img, int B, int L, void* stream);
+
+/* Sprite loader: uint8 NHWC [B,H,W,3] (sprites_*.npy as written by the reference's generate.py:858-904) -> fp32 NCHW
+ * in [-1,1], x/127.5 - 1 (PixelArtDataset.__getitem__, train_hybrid.py:181-182). */
+int lun_sprites_u8_to_f32(const void* u8_nhwc, float* out_nchw, int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -468,6 +468,85 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ mulv, const float* 
   dmulv[(size_t)b * 2 * L + L + l] = __float2bfloat16_rn(gl);
 }
 
+
+// ------------------------------------------------------------------------------------------- step losses
+// One pass over the reconstruction and the latent statistics (train_hybrid.py:859-862):
+//   sums[0] += sum (recon - x)^2        sums[1] += sum (1 + logvar - mu^2 - exp(logvar))
+__global__ void __launch_bounds__(256) vae_loss_fwd_kernel(const float* __restrict__ recon,
+                                                           const float* __restrict__ x,
+                                                           const float* __restrict__ mulv, float* __restrict__ sums,
+                                                           long n_img4, int B, int L) {
+  float a = 0.f, k = 0.f;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float4* r4 = reinterpret_cast<const float4*>(recon);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_img4; i += stride) {
+    const float4 r = __ldg(r4 + i), t = __ldg(x4 + i);
+    const float d0 = r.x - t.x, d1 = r.y - t.y, d2 = r.z - t.z, d3 = r.w - t.w;
+    a += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)B * L; i += stride) {
+    const int b = (int)(i / L), l = (int)(i % L);
+    const float mu = mulv[(size_t)b * 2 * L + l], lv = mulv[(size_t)b * 2 * L + L + l];
+    k += 1.f + lv - mu * mu - __expf(lv);
+  }
+  a = warp_sum(a);
+  k = warp_sum(k);
+  __shared__ float sa[8], sk[8];
+  if ((threadIdx.x & 31) == 0) {
+    sa[threadIdx.x >> 5] = a;
+    sk[threadIdx.x >> 5] = k;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tk = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      ta += sa[i];
+      tk += sk[i];
+    }
+    atomicAdd(sums, ta);
+    atomicAdd(sums + 1, tk);
+  }
+}
+// d_recon = g[0] * 2 (recon - x) / n_img;  d_mu = g[1] * mu / (B L);  d_logvar = g[1] * (-0.5)(1 - exp(logvar)) / (B L)
+// where g[0], g[1] (device scalars) are the upstream gradients of recon_loss and kl_loss.
+__global__ void __launch_bounds__(256) vae_loss_bwd_kernel(const float* __restrict__ recon,
+                                                           const float* __restrict__ x,
+                                                           const float* __restrict__ mulv,
+                                                           const float* __restrict__ g, float* __restrict__ drecon,
+                                                           float* __restrict__ dmulv, long n_img4, int B, int L) {
+  const float gr = g[0] * 2.f / (float)(n_img4 * 4), gk = g[1] / ((float)B * (float)L);
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float4* r4 = reinterpret_cast<const float4*>(recon);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* d4 = reinterpret_cast<float4*>(drecon);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_img4; i += stride) {
+    const float4 r = __ldg(r4 + i), t = __ldg(x4 + i);
+    d4[i] = make_float4(gr * (r.x - t.x), gr * (r.y - t.y), gr * (r.z - t.z), gr * (r.w - t.w));
+  }
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)B * L; i += stride) {
+    const int b = (int)(i / L), l = (int)(i % L);
+    const float mu = mulv[(size_t)b * 2 * L + l], lv = mulv[(size_t)b * 2 * L + L + l];
+    dmulv[(size_t)b * 2 * L + l] = gk * mu;
+    dmulv[(size_t)b * 2 * L + L + l] = gk * (-0.5f) * (1.f - __expf(lv));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- sprite loader
+// uint8 NHWC sprites [B,H,W,3] (the on-disk format of sprites_*.npy) -> fp32 NCHW in [-1,1]  (x/127.5 - 1,
+// train_hybrid.py:181-182)
+__global__ void __launch_bounds__(256) sprites_u8_to_f32_kernel(const unsigned char* __restrict__ u8,
+                                                                float* __restrict__ out, long n_pix, long hw) {
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  const long b = p / hw, r = p % hw;
+  const unsigned char* s = u8 + p * 3;
+  float* d = out + b * 3 * hw + r;
+  d[0] = (float)s[0] / 127.5f - 1.f;
+  d[hw] = (float)s[1] / 127.5f - 1.f;
+  d[2 * hw] = (float)s[2] / 127.5f - 1.f;
+}
+
 static int vae_blocks(int HW, int C, int B) {
   const int lanes = kVT / (C / 8);
   int per = (HW + lanes - 1) / lanes;
@@ -570,6 +649,30 @@ int lun_reparam_bwd(const float* mulv, const float* eps, const void* dz, const f
                     void* dmulv, int B, int L, void* stream) {
   reparam_bwd_kernel<<<(B * L + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mulv, eps, (const bf16*)dz, dmu, dlogvar,
                                                                             (bf16*)dmulv, B, L);
+  lun::note_launch(1);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_vae_loss_fwd(const float* recon, const float* images, const float* mulv, float* sums, long n_img, int B, int L,
+                     void* stream) {
+  if (n_img % 4) return LUN_E_SHAPE;
+  vae_loss_fwd_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(recon, images, mulv, sums, n_img / 4, B, L);
+  lun::note_launch(1);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_vae_loss_bwd(const float* recon, const float* images, const float* mulv, const float* g, float* drecon,
+                     float* dmulv, long n_img, int B, int L, void* stream) {
+  if (n_img % 4) return LUN_E_SHAPE;
+  vae_loss_bwd_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(recon, images, mulv, g, drecon, dmulv, n_img / 4, B, L);
+  lun::note_launch(1);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_sprites_u8_to_f32(const void* u8_nhwc, float* out_nchw, int B, int H, int W, void* stream) {
+  const long n = (long)B * H * W;
+  sprites_u8_to_f32_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)u8_nhwc,
+                                                                                    out_nchw, n, (long)H * W);
   lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }

@@ -425,3 +425,58 @@ class _VAEFn(torch.autograd.Function):
         grads = tuple(g[n].view_as(p) if g[n].shape != p.shape else g[n]
                       for n, p in zip(ctx.names, vae.parameters()))
         return (None, None, None) + grads
+
+
+# ====================================================================================================== step losses
+class _VaeLossFn(torch.autograd.Function):
+    """(recon, images, mu, logvar) -> (recon_loss, kl_loss): MSE mean and -0.5*mean(1+lv-mu^2-e^lv)
+    (train_hybrid.py:859-862) in one kernel, gradients in a second one."""
+
+    @staticmethod
+    def forward(ctx, recon, images, mu, logvar):
+        lib = _capi.lib()
+        B, L = mu.shape
+        recon = recon.float().contiguous()
+        images = images.float().contiguous()
+        if (mu.dtype == torch.float32 and logvar.dtype == torch.float32 and mu.stride() == (2 * L, 1)
+                and logvar.stride() == (2 * L, 1) and logvar.data_ptr() == mu.data_ptr() + 4 * L):
+            mulv = torch.as_strided(mu, (B, 2 * L), (2 * L, 1))     # mu | logvar already packed by the fused fc
+        else:
+            mulv = torch.cat([mu.float(), logvar.float()], 1).contiguous()
+        sums = torch.zeros(2, device=recon.device, dtype=torch.float32)
+        check(lib.lun_vae_loss_fwd(recon.data_ptr(), images.data_ptr(), mulv.data_ptr(), sums.data_ptr(),
+                                   recon.numel(), B, L, _stream()), "lun_vae_loss_fwd")
+        ctx.save_for_backward(recon, images, mulv)
+        scale = torch.tensor([1.0 / recon.numel(), -0.5 / (B * L)], device=recon.device)
+        out = sums * scale
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_recon, g_kl):
+        lib = _capi.lib()
+        recon, images, mulv = ctx.saved_tensors
+        B, L2 = mulv.shape
+        L = L2 // 2
+        # kl = -0.5/(BL) * sum(...): fold the -0.5 into the kernel's analytic form: d kl/d mu = mu/(BL), etc.
+        g = torch.stack([g_recon if g_recon is not None else torch.zeros((), device=recon.device),
+                         g_kl if g_kl is not None else torch.zeros((), device=recon.device)]).float().contiguous()
+        d_recon = torch.empty_like(recon)
+        d_mulv = torch.empty_like(mulv)
+        check(lib.lun_vae_loss_bwd(recon.data_ptr(), images.data_ptr(), mulv.data_ptr(), g.data_ptr(),
+                                   d_recon.data_ptr(), d_mulv.data_ptr(), recon.numel(), B, L, _stream()),
+              "lun_vae_loss_bwd")
+        return d_recon, None, d_mulv[:, :L], d_mulv[:, L:]
+
+
+def vae_losses(recon, images, mu, logvar):
+    """recon_loss (MSE mean) and kl_loss exactly as train_hybrid.py:859-862, through the fused CUDA kernels."""
+    return _VaeLossFn.apply(recon, images, mu, logvar)
+
+
+def sprites_to_tensor(u8_nhwc):
+    """uint8 NHWC sprites on the GPU -> fp32 NCHW in [-1,1] (PixelArtDataset normalisation, train_hybrid.py:181-182)."""
+    B, H, W, _ = u8_nhwc.shape
+    out = torch.empty(B, 3, H, W, device=u8_nhwc.device, dtype=torch.float32)
+    check(_capi.lib().lun_sprites_u8_to_f32(u8_nhwc.contiguous().data_ptr(), out.data_ptr(), B, H, W, _stream()),
+          "lun_sprites_u8_to_f32")
+    return out

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from torch.optim.lr_scheduler import CosineAnnealingWarmRestarts
 
 from .lunar_evaluator import LunarMoETeacher
-from .lunar_generate import LunarisCoreVAE
+from .lunar_generate import LunarisCoreVAE, sprites_to_tensor, vae_losses
 
 METRIC_KEYS = ("recon_loss", "kl_loss", "quality_loss", "pg_loss", "semantic_reward", "quality_reward", "baseline",
                "advantage", "vae_loss", "teacher_loss", "total_loss", "quality_scores")
@@ -166,8 +166,10 @@ class SpriteData:
         order = order.reshape(n, self.world, self.bs)[:, self.rank]
         for idx in order:
             u8 = torch.from_numpy(np.ascontiguousarray(self.arr[np.sort(idx)]))
-            x = u8.pin_memory().to(device, non_blocking=True) if device.type == "cuda" else u8
-            yield x.permute(0, 3, 1, 2).float().div_(127.5).sub_(1.0)
+            if device.type == "cuda":
+                yield sprites_to_tensor(u8.pin_memory().to(device, non_blocking=True))
+            else:
+                yield u8.permute(0, 3, 1, 2).float().div_(127.5).sub_(1.0)
 
 
 # ====================================================================================================== trainer
@@ -227,8 +229,7 @@ class TrainingManager:
         recon, mu, logvar = self.vae(images)
         with torch.no_grad():
             self.teacher(images)                                        # pass A: BN statistics / RNG position only
-        recon_loss = F.mse_loss(recon, images, reduction='mean')
-        kl_loss = -0.5 * torch.mean(1 + logvar - mu.pow(2) - logvar.exp())
+        recon_loss, kl_loss = vae_losses(recon, images, mu, logvar)     # fused MSE + KL (train_hybrid.py:859-862)
         teacher_eval = self.teacher(recon.detach())                     # pass B
         quality_scores = teacher_eval['quality_scores']
         semantic_score = teacher_eval['semantic_score']

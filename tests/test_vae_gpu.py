@@ -15,3 +15,31 @@ def test_vae_forward_backward_and_sampling(cuda_dev):
     assert rep["grad_rel_max"] <= 3 * rep["cal_grad_rel_max"] + 0.01, rep["grad_worst"]
     assert rep["ratio_worst"][0][1] < 4.0, rep["ratio_worst"]
     assert rep["sample"] < 0.05
+
+
+@pytest.mark.gpu
+def test_fused_losses_and_sprite_loader_match_torch(cuda_dev):
+    """lun_vae_loss_fwd/bwd vs F.mse_loss + the KL expression of train_hybrid.py:859-862 (fp32: rtol 1e-5), and the
+    uint8 loader kernel vs x/127.5 - 1 (bit exact)."""
+    import torch
+    import torch.nn.functional as F
+    from lunaris_orion_b200.lunar_generate import sprites_to_tensor, vae_losses
+    g = torch.Generator().manual_seed(1)
+    B, L = 4, 64
+    recon = torch.tanh(torch.randn(B, 3, 128, 128, generator=g)).to(cuda_dev).requires_grad_(True)
+    x = (torch.rand(B, 3, 128, 128, generator=g) * 2 - 1).to(cuda_dev)
+    mulv = torch.randn(B, 2 * L, generator=g).to(cuda_dev).requires_grad_(True)
+    mu, lv = mulv[:, :L], mulv[:, L:]
+    r1, k1 = vae_losses(recon, x, mu, lv)
+    (0.7 * r1 + 0.1 * k1).backward()
+    g_recon, g_mulv = recon.grad.clone(), mulv.grad.clone()
+    recon.grad = mulv.grad = None
+    r2 = F.mse_loss(recon, x)
+    k2 = -0.5 * torch.mean(1 + lv - mu.pow(2) - lv.exp())
+    (0.7 * r2 + 0.1 * k2).backward()
+    assert torch.allclose(r1, r2, rtol=1e-5) and torch.allclose(k1, k2, rtol=1e-5)
+    assert torch.allclose(g_recon, recon.grad, rtol=1e-5, atol=1e-10)
+    assert torch.allclose(g_mulv, mulv.grad, rtol=1e-5, atol=1e-9)
+    u8 = torch.randint(0, 256, (3, 128, 128, 3), generator=g, dtype=torch.uint8).to(cuda_dev)
+    # the reference normalises on the CPU inside PixelArtDataset (true division); compare with that, bit for bit
+    assert torch.equal(sprites_to_tensor(u8).cpu(), u8.cpu().permute(0, 3, 1, 2).float() / 127.5 - 1.0)
