@@ -16,11 +16,14 @@
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 #include "launch_count.cuh"
+#include <stdlib.h>
 
 namespace lun {
 
 constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kAReuseBox = 130 * 128;   // 130 pixel rows (one halo pixel on each side) x 64 bf16
+constexpr int kAReuseSlot = 17 * 1024;  // rounded up so the weight tiles behind it stay 1024-byte aligned
 
 struct __align__(16) PipeBars {
   uint64_t full[8];
@@ -31,15 +34,24 @@ struct __align__(16) PipeBars {
   uint32_t pad;
 };
 
+// CG = 1: one CTA per 128-pixel tile. CG = 2: a CTA pair (cluster of 2) computes a 256-pixel x block_n tile with
+// tcgen05.mma.cta_group::2 - each CTA loads its own 128 pixel rows of A and HALF of the weight tile, the leader CTA
+// issues the MMAs, both CTAs drain their own 128 accumulator rows.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmO, const ConvGeom g, const float* __restrict__ bias, void* __restrict__ out,
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const ConvGeom g, const float* __restrict__ bias, void* __restrict__ out,
                   float* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int block_n = g.block_n;
-  const int b_bytes = block_n * 128;
-  const int stage_bytes = kABytes + b_bytes;
+  const int b_bytes = block_n / CG * 128;          // this CTA's share of the weight tile
+  // a_reuse: a stage holds one (TW+2)-row A box (17 KB slot) and the weight tiles of the 3 dx taps that share it
+  const int a_bytes = g.a_reuse ? kAReuseSlot : kABytes;
+  const int taps_per_stage = g.a_reuse ? 3 : 1;
+  const int stage_bytes = a_bytes + taps_per_stage * b_bytes;
+  const int stage_tx = (g.a_reuse ? kAReuseBox : kABytes) + taps_per_stage * b_bytes;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const int stages = g.stages;
   uint8_t* s_stage = smem + stages * stage_bytes;  // 2 x 8 KB output staging tiles (128 rows x 64 B, 64B swizzle)
   PipeBars* bars = reinterpret_cast<PipeBars*>(s_stage + kABytes);
@@ -51,9 +63,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int n_blocks = g.Cout / block_n;
   const int m_tiles = g.ntb * g.nth * g.ntw;
-  const int total_tiles = m_tiles * n_blocks;
+  const int total_tiles = m_tiles / CG * n_blocks;  // work items (tile pairs when CG == 2)
+  const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
   const int kchunks = (g.Cin + 63) >> 6;   // a ragged last chunk is zero-filled by TMA (both operands)
-  const int ksteps = g.ntaps * kchunks;
+  const int ksteps = g.ntaps / taps_per_stage * kchunks;   // pipeline steps per tile
   const uint32_t tmem_cols = (2 * block_n <= 32) ? 32u : (2 * block_n <= 64) ? 64u : (2 * block_n <= 128) ? 128u
                              : (2 * block_n <= 256) ? 256u : 512u;
 
@@ -67,7 +80,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tfull[i], 1);
-      mbar_init(&bars->tempty[i], 8);
+      mbar_init(&bars->tempty[i], 8 * CG);
     }
     fence_barrier_init();
   }
@@ -76,11 +89,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = threadIdx.x; i < 2 * g.Cout; i += kThreads) s_stats[i] = 0.f;
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, tmem_cols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(&bars->tmem_base, tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&bars->tmem_base, tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();      // peer barriers must be initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -88,25 +107,30 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ TMA producer (lane 0: A tile, lane 1: B tile)
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_item; tile < total_tiles; tile += item_stride) {
       const int n_blk = tile % n_blocks;
-      int m = tile / n_blocks;
+      int m = (tile / n_blocks) * CG + cta_rank;
       const int tw = m % g.ntw;
       m /= g.ntw;
       const int th = m % g.nth;
       const int tb = m / g.nth;
       const int w0 = tw * g.TW * g.in_mul, h0 = th * g.TH * g.in_mul, b0 = tb * g.TB;
-      for (int t = 0; t < g.ntaps; ++t) {
+      for (int t = 0; t < g.ntaps; t += taps_per_stage) {
         const int cw = w0 + g.dx[t], ch = h0 + g.dy[t];
-        const int wrow = g.slab[t] * g.Cout + n_blk * block_n;
+        const int nsel = n_blk * block_n + cta_rank * (block_n / CG);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&bars->empty[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           if (lane == 0) {
-            mbar_expect_tx(&bars->full[s], stage_bytes);
-            tma_load_4d(sa, &tmA, &bars->full[s], kc * 64, cw, ch, b0);
-          } else if (lane == 1) {
-            tma_load_2d(sa + kABytes, &tmB, &bars->full[s], kc * 64, wrow);
+            if (cta_rank == 0) mbar_expect_tx(&bars->full[s], CG * stage_tx);
+            const CUtensorMap* ma = g.a_reuse ? &tmA2 : &tmA;
+            if (CG == 2) tma_load_4d_pair(sa, ma, &bars->full[s], kc * 64, cw, ch, b0);
+            else tma_load_4d(sa, ma, &bars->full[s], kc * 64, cw, ch, b0);
+          } else if (lane <= taps_per_stage) {
+            const int j = lane - 1;
+            const int wrow = g.slab[t + j] * g.Cout + nsel;
+            if (CG == 2) tma_load_2d_pair(sa + a_bytes + j * b_bytes, &tmB, &bars->full[s], kc * 64, wrow);
+            else tma_load_2d(sa + a_bytes + j * b_bytes, &tmB, &bars->full[s], kc * 64, wrow);
           }
           if (++s == stages) { s = 0; ph ^= 1; }
         }
@@ -114,34 +138,47 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, block_n, false, false);
-    int s = 0;
-    uint32_t ph = 0;
-    int acc = 0;
-    uint32_t pacc = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&bars->tempty[acc], pacc ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * block_n;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(&bars->full[s], ph);
+    if (cta_rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(128 * CG, block_n, false, false);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t pacc = 0;
+      for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+        mbar_wait(&bars->tempty[acc], pacc ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
-          const uint64_t adesc = make_smem_desc_sw128(sa, 0, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 0, 1024);
+        const uint32_t tmem_d = tmem_base + acc * block_n;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&bars->full[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + s * stage_bytes);
+            for (int j = 0; j < taps_per_stage; ++j) {
+              // tap j of the filter row reads the same A box shifted by j pixel rows (128 bytes each)
+              // (the 128B swizzle is a function of absolute smem address bits, so a 128-byte row offset of the
+              // start address needs no descriptor base_offset as long as the box itself is 1024-byte aligned)
+              const uint64_t adesc = make_smem_desc_sw128(sa + j * 128, 0, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(sa + a_bytes + j * b_bytes, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 16 bf16 (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                // advance 16 bf16 (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
+                if (CG == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | j | k) != 0);
+                else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | j | k) != 0);
+              }
+            }
+            if (CG == 2) {
+              umma_commit_pair(&bars->empty[s]);
+              if (ks == ksteps - 1) umma_commit_pair(&bars->tfull[acc]);
+            } else {
+              umma_commit(&bars->empty[s]);
+              if (ks == ksteps - 1) umma_commit(&bars->tfull[acc]);
+            }
           }
-          umma_commit(&bars->empty[s]);
-          if (ks == ksteps - 1) umma_commit(&bars->tfull[acc]);
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == stages) { s = 0; ph ^= 1; }
+        if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
-      if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
@@ -164,9 +201,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t pacc = 0;
     bool store_pending = false;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_item; tile < total_tiles; tile += item_stride) {
       const int n_blk = tile % n_blocks;
-      int m = tile / n_blocks;
+      int m = (tile / n_blocks) * CG + cta_rank;
       const int tw = m % g.ntw;
       m /= g.ntw;
       const int th = m % g.nth;
@@ -284,7 +321,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // every TMEM read of this accumulator stage by this warp has completed (tmem_ld_wait above)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(&bars->tempty[acc], 0);   // the leader's MMA warp owns the accumulator hand-back
+        else mbar_arrive(&bars->tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
     if (store_pending && half_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -295,10 +335,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -388,40 +430,93 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   if (g.Cout > 2048 && (g.flags & EPI_STATS)) return 6;
   if (!(g.flags & EPI_OUT_F32) && (g.ldo % 8 || g.o_coff % 8)) return 7;
 
-  CUtensorMap tmA, tmB, tmO;
-  // coalesced asynchronous output path: bf16, dense pixel mapping, 64-channel boxes
+  CUtensorMap tmA, tmA2, tmB, tmO;
+  const int m_tiles = g.ntb * g.nth * g.ntw;
+  // CTA pairs for the big tiles: full 256-wide N block, an even number of pixel tiles, enough work for every pair
+  const int sms = num_sms();
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char* e = getenv("LUN_CONV_PAIR");
+    pair_mode = e ? atoi(e) : 1;
+  }
+  const int cg = (pair_mode && g.block_n == 256 && m_tiles % 2 == 0 && sms % 2 == 0 &&
+                  (long)m_tiles / 2 * (g.Cout / g.block_n) >= sms / 2) ? 2 : 1;
+  // A-tile reuse: taps sorted by (dy, dx) come in runs of 3 with equal dy and consecutive dx, one image row per tile
+  {
+    for (int i = 1; i < g.ntaps; ++i)            // insertion sort of the tap list by (dy, dx)
+      for (int j = i; j > 0 && (g.dy[j] < g.dy[j - 1] || (g.dy[j] == g.dy[j - 1] && g.dx[j] < g.dx[j - 1])); --j) {
+        int t;
+        t = g.dy[j]; g.dy[j] = g.dy[j - 1]; g.dy[j - 1] = t;
+        t = g.dx[j]; g.dx[j] = g.dx[j - 1]; g.dx[j - 1] = t;
+        t = g.slab[j]; g.slab[j] = g.slab[j - 1]; g.slab[j - 1] = t;
+      }
+    static int reuse_mode = -1;
+    if (reuse_mode < 0) {
+      const char* e = getenv("LUN_CONV_AREUSE");
+      reuse_mode = e ? atoi(e) : 1;
+    }
+    bool ok = reuse_mode && cg == 2 && g.ntaps % 3 == 0 && g.TW == 128 && g.TH == 1 && g.TB == 1 && g.in_mul == 1 &&
+              g.block_n == 256;
+    for (int i = 0; ok && i < g.ntaps; i += 3)
+      ok = g.dy[i + 1] == g.dy[i] && g.dy[i + 2] == g.dy[i] && g.dx[i + 1] == g.dx[i] + 1 && g.dx[i + 2] == g.dx[i] + 2;
+    g.a_reuse = ok ? 1 : 0;
+  }
+  // coalesced asynchronous output path: bf16, dense pixel mapping, 32-channel boxes
   if (!(g.flags & EPI_OUT_F32) && g.o_mul == 1)
     g.flags |= EPI_TMA_STORE;
   else
     g.flags &= ~EPI_TMA_STORE;
   int rc = make_tmap_nhwc(&tmA, x, XB, XH, XW, g.Cin, g.TW * g.in_mul, g.TH * g.in_mul, g.TB, g.in_mul);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, wpk, (long)nslabs * g.Cout, g.Cin, g.block_n);
+  if (g.a_reuse) {
+    rc = make_tmap_nhwc(&tmA2, x, XB, XH, XW, g.Cin, g.TW + 2, 1, 1, 1);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
+  }
+  rc = make_tmap_2d(&tmB, wpk, (long)nslabs * g.Cout, g.Cin, g.block_n / cg);
   if (rc) return rc;
-
   if (g.flags & EPI_TMA_STORE) {
     rc = make_tmap_nhwc_ex(&tmO, out, g.GB, g.OH, g.OW, g.ldo, 32, g.TW, g.TH, g.TB, 1, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   } else {
     tmO = tmA;
   }
-  const int stage_bytes = kABytes + g.block_n * 128;
+  const int stage_bytes = g.a_reuse ? kAReuseSlot + 3 * (g.block_n / cg * 128) : kABytes + g.block_n / cg * 128;
   const int extra = kABytes + (int)sizeof(PipeBars) + g.Cout * 4 + ((g.flags & EPI_STATS) ? 2 * g.Cout * 4 : 0) + 1024;
   int stages = (227 * 1024 - extra) / stage_bytes;
   if (stages > 8) stages = 8;
   g.stages = stages;
   const int smem_bytes = stages * stage_bytes + extra;
-  static int configured = 0;
-  if (configured < smem_bytes) {
-    if (cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(conv_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess)
       return 8;
-    configured = 227 * 1024;
+    configured = true;
   }
-  const int total_tiles = g.ntb * g.nth * g.ntw * (g.Cout / g.block_n);
-  int grid = num_sms();
-  if (grid > total_tiles) grid = total_tiles;
-  conv_fprop_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmO, g, bias, out, stats);
+  const int total_items = m_tiles / cg * (g.Cout / g.block_n);
+  int grid = sms;
+  if (grid > total_items * cg) grid = total_items * cg;
+  if (cg == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, conv_fprop_kernel<2>, tmA, tmA2, tmB, tmO, g, bias, out, stats) != cudaSuccess) return 9;
+  } else {
+    conv_fprop_kernel<1><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmO, g, bias, out, stats);
+  }
   note_launch(1);
   return cudaGetLastError() == cudaSuccess ? 0 : 9;
 }

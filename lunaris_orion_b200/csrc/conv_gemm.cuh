@@ -29,6 +29,9 @@ struct ConvGeom {
   int dy[kMaxTaps], dx[kMaxTaps], slab[kMaxTaps];
   int Cin, Cout, block_n;
   int stages;
+  // A-tile reuse across the dx taps of a filter row (3 consecutive taps with equal dy and dx, dx+1, dx+2, full-width
+  // row tiles): one TW+2-pixel A box per (dy, channel chunk) feeds three MMA groups through descriptor row offsets.
+  int a_reuse;
   // output tensor [*, OH, OW, ldo]; grid point (b,h,w) -> pixel (b, h*o_mul + o_ph, w*o_mul + o_pw), channel o_coff + n
   int OH, OW, o_mul, o_ph, o_pw, ldo, o_coff;
   int flags;
