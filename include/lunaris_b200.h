@@ -109,6 +109,19 @@ int lun_attn_ref_rows_split_bf16(const void* q_small, const void* kv, void* att_
  * i < N/32 - 1, else the 32 tokens of the last chunk (lunar_evaluator.py:203-216). */
 int lun_gather_query_rows_bf16(const void* x, void* out, int B, int N, int C, int nq_pad, void* stream);
 
+/* As-executed attention WITHOUT forming K or V. Only one query per 32-token chunk survives the reference's
+ * chunk-index scatter, so with qt = (Wk_h^T Wq_h) x_q / sqrt(hd) + Wk_h^T bq_h / sqrt(hd) (a small GEMM, head-major
+ * [B, nq_pad, 8*C]) the scores are qt_h . x_j and the head output is Wv_h (sum_j p_j x_j) + bv_h. This kernel computes
+ * xbar[b,i,h,:] = sum_j softmax_j(qt[b,i,h,:] . x_j) x_j over the 32 tokens of the row's chunk, where
+ * x = drop2d(bn(y)) is formed on load from the pre-BatchNorm tensor y (scale/shift [C], mask2d [B,C] or null).
+ * Same function as lun_attn_ref_rows_bf16 composed with the qkv conv (lunar_evaluator.py:153-156,203-216). */
+int lun_attn_fold_rows_bf16(const void* y, const float* scale, const float* shift, const float* mask2d,
+                            const void* qt, void* xbar, int B, int N, int C, int heads, int nq_pad,
+                            unsigned long long seed, float drop_p, void* stream);
+/* out[b,i,:] = drop2d(bn(y[b, qtok(i), :])) — the surviving query rows with the attention-input affine applied. */
+int lun_gather_query_rows_affine_bf16(const void* y, const float* scale, const float* shift, const float* mask2d,
+                                      void* out, int B, int N, int C, int nq_pad, void* stream);
+
 /* y[b,p,:] = proj_drop( p < nq ? proj_small[b,p,:] : bias )  (lunar_evaluator.py:224-225 on the mostly-zero input). */
 int lun_proj_expand_bf16(const void* proj_small, const float* bias, void* y, int B, int HW, int C, int nq, int nq_pad,
                          unsigned long long seed, float drop_p, void* stream);

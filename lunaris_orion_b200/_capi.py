@@ -69,6 +69,10 @@ SIGNATURES = {
     "lun_attn_ref_rows_split_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_float,
                                      c_void_p],
     "lun_gather_query_rows_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "lun_attn_fold_rows_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_int, c_u64, c_float, c_void_p],
+    "lun_gather_query_rows_affine_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_int, c_void_p],
     "lun_proj_expand_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_float,
                              c_void_p],
     "lun_proj_bwd_gather_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_float,

@@ -89,7 +89,9 @@ class PixelArtAttention(nn.Module):
 
     def forward(self, x):
         B, C, H, W = x.shape
-        h2, _ = _attention_forward(self, _to_nhwc(x), B, H, W, self.training, save=False)
+        one, zero = torch.ones(C, device=x.device), torch.zeros(C, device=x.device)
+        h2, _ = _attention_forward(self, _to_nhwc(x).view(B, H * W, C), one, zero, None, B, H, W, self.training,
+                                   save=False)
         return _to_nchw(h2, B, H, W)
 
 
@@ -324,37 +326,67 @@ def _fe_forward(fe, x, n_updates):
     return feats, pooled
 
 
-def _attention_forward(att, x1, B, H, W, training, save):
-    """PixelArtAttention.forward as executed (lunar_evaluator.py:189-227): qkv 1x1 conv, block-local attention for the
-    N/32+31 rows that survive the chunk-index scatter, proj on those rows, bias elsewhere, proj_drop.
-    x1: NHWC bf16 [B,HW,C]. Returns conv2's input h2 [B,HW,C] and what proj's backward needs."""
+_fold_cache = {}
+
+
+def _folded_attention_weights(att):
+    """Weight-only precompute for the K/V-free attention (refreshed when qkv changes; in reference mode it never
+    does - qkv receives no gradient): Mq [8C, C] = Wk_h^T Wq_h / sqrt(hd) stacked over heads, cq [8C] = Wk_h^T bq_h /
+    sqrt(hd), and the value projection as a block-diagonal [C, 8C] matrix. bf16 operands, fp32 products."""
+    w, bq = att.qkv.weight, att.qkv.bias
+    key = id(att)
+    ver = (w._version, bq._version, str(w.device))
+    ent = _fold_cache.get(key)
+    if ent is not None and ent[0] == ver and ent[2] is att:     # identity check: ids are recycled after GC
+        return ent[1]
+    C, h = att.qkv.in_channels, att.num_heads
+    hd = C // h
+    wf = w.detach().reshape(3, h, hd, C).to(torch.bfloat16).float()          # [3][head][d][c]
+    bf = bq.detach().reshape(3, h, hd).float()
+    scale = float(torch.tensor(hd ** -0.5).to(torch.bfloat16))
+    mq = torch.einsum("hdk,hdc->hkc", wf[1], wf[0]).mul_(scale).reshape(h * C, C)
+    cq = torch.einsum("hdk,hd->hk", wf[1], bf[0]).mul_(scale).reshape(h * C)
+    wv = torch.zeros(C, h * C, device=w.device)
+    for i in range(h):
+        wv[i * hd:(i + 1) * hd, i * C:(i + 1) * C] = wf[2, i]
+    out = (mq.to(torch.bfloat16).contiguous(), cq.contiguous(), wv.to(torch.bfloat16).contiguous(),
+           bf[2].reshape(C).contiguous())
+    _fold_cache[key] = (ver, out, att)
+    return out
+
+
+def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save):
+    """PixelArtAttention.forward as executed (lunar_evaluator.py:189-227) on the pre-BatchNorm conv1 output y1
+    [B,HW,C] (x1 = drop2d(bn(y1)) is applied on load, never written). Only N/32+31 rows survive the reference's
+    chunk-index scatter; for those rows the K and V projections are folded into the query / output side (see
+    csrc/attn_fold.cu), then proj runs on the surviving rows, bias elsewhere, then proj_drop.
+    Returns conv2's input h2 [B,HW,C] and what proj's backward needs."""
     lib = _capi.lib()
     C = att.qkv.in_channels
     HW = H * W
     nq = HW // _CHUNK + _CHUNK - 1
     nq_pad = (nq + 7) // 8 * 8
+    heads = att.num_heads
     p_attn = att.attn_drop.p if training else 0.0
     p_proj = att.proj_drop.p if training else 0.0
-    att._touch_rel_pos(H, W, x1.device)
-    # Only N/32+31 query rows survive the reference's chunk-index scatter: K and V are computed for every token, Q
-    # only for those rows (identical results, one third of the qkv FLOPs and output bytes removed).
-    kv = ops.conv2d_fprop(x1.view(B, H, W, C), _packed(att.qkv.weight, "kv_fwd"), 1, 1, 0,
-                          bias=_packed(att.qkv.bias, "kv_f32"))
-    xq = torch.zeros(B, nq_pad, C, device=x1.device, dtype=torch.bfloat16)
-    check(lib.lun_gather_query_rows_bf16(x1.data_ptr(), xq.data_ptr(), B, HW, C, nq_pad, _stream()),
-          "lun_gather_query_rows_bf16")
-    q_small = ops.linear_fprop(xq.view(B * nq_pad, C), _packed(att.qkv.weight, "q_fwd").view(C, C),
-                               _packed(att.qkv.bias, "q_f32"), out_f32=False)
-    att_small = torch.zeros(B, nq_pad, C, device=x1.device, dtype=torch.bfloat16)
-    check(lib.lun_attn_ref_rows_split_bf16(q_small.data_ptr(), kv.data_ptr(), att_small.data_ptr(), B, HW, C,
-                                           att.num_heads, nq_pad, _cpu_seed() if p_attn > 0 else 0, float(p_attn),
-                                           _stream()), "lun_attn_ref_rows_split_bf16")
-    del kv
+    att._touch_rel_pos(H, W, y1.device)
+    mq, cq, wv_bd, bv = _folded_attention_weights(att)
+    xq = torch.zeros(B, nq_pad, C, device=y1.device, dtype=torch.bfloat16)
+    check(lib.lun_gather_query_rows_affine_bf16(y1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), _p(m1), xq.data_ptr(),
+                                                B, HW, C, nq_pad, _stream()), "lun_gather_query_rows_affine_bf16")
+    qt = ops.linear_fprop(xq.view(B * nq_pad, C), mq, cq, out_f32=False)              # [B*nq_pad, heads*C]
+    xbar = torch.zeros(B * nq_pad, heads * C, device=y1.device, dtype=torch.bfloat16)
+    check(lib.lun_attn_fold_rows_bf16(y1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), _p(m1), qt.data_ptr(),
+                                      xbar.data_ptr(), B, HW, C, heads, nq_pad, _cpu_seed() if p_attn > 0 else 0,
+                                      float(p_attn), _stream()), "lun_attn_fold_rows_bf16")
+    att_small = ops.linear_fprop(xbar, wv_bd, bv, out_f32=False).view(B, nq_pad, C)
+    if nq_pad > nq:
+        att_small[:, nq:].zero_()
     wp = _packed(att.proj.weight, "fwd")
     proj_small = ops.linear_fprop(att_small.view(B * nq_pad, C), wp.view(C, C), _packed(att.proj.bias, "f32"),
                                   out_f32=False)
     seed = _cpu_seed() if p_proj > 0 else 0
-    h2 = torch.empty(B, HW, C, device=x1.device, dtype=torch.bfloat16)
+    h2 = torch.empty(B, HW, C, device=y1.device, dtype=torch.bfloat16)
     check(lib.lun_proj_expand_bf16(proj_small.data_ptr(), _packed(att.proj.bias, "f32").data_ptr(), h2.data_ptr(), B,
                                    HW, C, nq, nq_pad, seed, float(p_proj), _stream()), "lun_proj_expand_bf16")
     saved = dict(att_small=att_small, seed=seed, p_proj=p_proj, nq=nq, nq_pad=nq_pad) if save else None
@@ -375,10 +407,8 @@ def _block_forward(blk, x, B, H, W, training, n_updates, save, pool):
                           act_leaky=True, stats=st, slope=_SLOPE)
     sc1, sh1 = _bn_train(bn1, st, B * HW, n_updates)[:2] if training else _bn_eval(bn1)
     m1 = _drop2d_mask(B, C, p2d, dev) if p2d > 0 else None
-    x1 = _affine(y1.view(B, HW, C), B, HW, C, sc1, sh1, mask2d=m1)
+    h2, att_saved = _attention_forward(blk.attention, y1.view(B, HW, C), sc1, sh1, m1, B, H, W, training, save)
     del y1
-    h2, att_saved = _attention_forward(blk.attention, x1, B, H, W, training, save)
-    del x1
 
     st = torch.zeros(2 * C, device=dev) if training else None
     y2 = ops.conv2d_fprop(h2.view(B, H, W, C), _packed(c2.weight, "fwd"), 3, 1, 1, bias=_packed(c2.bias, "f32"),

@@ -115,3 +115,27 @@ def test_attention_rows_split_equals_full_qkv_and_oracle(cuda_dev):
     ref = ref.permute(0, 2, 3, 1).reshape(B, N, C)
     assert ref[:, nq:].abs().max().item() == 0.0                       # everything past row nq stays zero
     assert tc.rel_err(full[:, :nq], ref[:, :nq]) < 2e-2
+
+
+@pytest.mark.gpu
+def test_folded_attention_module_matches_oracle(cuda_dev):
+    """PixelArtAttention.forward (K/V-free folded path, csrc/attn_fold.cu) vs the oracle's qkv conv + as-executed
+    local attention + proj (lunar_evaluator.py:146-227), eval mode. Tolerance 2 % of max |ref| (bf16 path)."""
+    import torch.nn.functional as F
+    from lunaris_orion_b200 import lunar_evaluator as le
+    from oracle import restatement as R
+    torch.manual_seed(4)
+    att = le.PixelArtAttention(128, dropout=0.0).to(cuda_dev).eval()
+    with torch.no_grad():
+        att.qkv.bias.normal_(0, 0.2)
+        att.proj.bias.normal_(0, 0.2)
+    x = torch.randn(2, 128, 64, 64, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        mine = att(x.to(cuda_dev)).cpu()
+        w = {k: v.detach().cpu().float() for k, v in att.state_dict().items() if v is not None}
+        qkv = F.conv2d(x, w["qkv.weight"], w["qkv.bias"])
+        ref = F.conv2d(R.local_attention(qkv, "reference"), w["proj.weight"], w["proj.bias"])
+    assert tc.rel_err(mine, ref) < 2e-2
+    nq = 64 * 64 // 32 + 31
+    flat = mine.permute(0, 2, 3, 1).reshape(2, -1, 128)
+    assert torch.allclose(flat[:, nq:], w["proj.bias"].to(torch.bfloat16).float().expand_as(flat[:, nq:]))
