@@ -51,6 +51,8 @@ struct WgradGeom {
   int stages;
   int splits;          // split-K factor (k-chunks are dealt round-robin to splits)
   int dy_mul, dy_ph, dy_pw;  // dY pixel = grid*dy_mul + phase  (transposed-conv phases)
+  // reuse3: the three dx taps of a filter row share one (TW+2)-pixel X box; a unit accumulates 3 tiles (one per tap)
+  int reuse3;
 };
 
 }  // namespace lun

@@ -12,6 +12,7 @@
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 #include "launch_count.cuh"
+#include <stdlib.h>
 
 namespace lun {
 
@@ -22,6 +23,8 @@ bool tile_grid(int GB, int GH, int GW, int pixels, int* TB, int* TH, int* TW);
 
 constexpr int kWgThreads = 192;
 constexpr int kWgABytes = 128 * 128;  // 64 pixels x 128 channels bf16
+constexpr int kWgXBox = 66 * 128;     // reuse3: 66 pixel rows (one halo pixel each side) x 64 channels
+constexpr int kWgXSlot = 9 * 1024;    // ... in a 1024-byte aligned slot
 
 struct __align__(8) WgBars {
   uint64_t full[8];
@@ -38,26 +41,38 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+// CG = 2: a CTA pair accumulates a 256 (Cout) x block_n (Cin) tile with tcgen05.mma.cta_group::2 - each CTA loads its own
+// 128 Cout columns of dY and HALF of the Cin columns of X, the leader issues the MMAs, both drain their 128 rows.
+template <int CG>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
-                  const WgradGeom g, float* __restrict__ dw) {
+                  const __grid_constant__ CUtensorMap tmX2, const WgradGeom g, float* __restrict__ dw) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int block_n = g.block_n;
-  const int b_bytes = block_n * 128;
+  const bool r3 = g.reuse3 != 0;
+  const int xslot = r3 ? kWgXSlot : 8192;                 // bytes between the 64-channel atoms of the X operand
+  const int nb_cta = block_n / CG;                        // Cin columns of the X operand loaded by this CTA
+  const int b_bytes = nb_cta / 64 * xslot;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const int stage_bytes = kWgABytes + b_bytes;
+  const int stage_tx = kWgABytes + nb_cta / 64 * (r3 ? kWgXBox : 8192);
+  const int tps = r3 ? 3 : 1;                             // taps accumulated per unit
+  const int nacc = r3 ? 1 : 2;                            // accumulator sets in TMEM
   const int stages = g.stages;
   WgBars* bars = reinterpret_cast<WgBars*>(smem + stages * stage_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_blocks = (g.Cout + 127) / 128;
+  const int m_blocks = (g.Cout + 128 * CG - 1) / (128 * CG);
   const int n_blocks = (g.Cin + block_n - 1) / block_n;
-  const int tiles = m_blocks * n_blocks * g.ntaps;
+  const int first_unit = blockIdx.x / CG, unit_stride = gridDim.x / CG;
+  const int tiles = m_blocks * n_blocks * (g.ntaps / tps);
   const int units = tiles * g.splits;
   const int chunks = g.ntb * g.nth * g.ntw;  // 64-pixel k-chunks
-  const uint32_t tmem_cols = (2 * block_n <= 64) ? 64u : (2 * block_n <= 128) ? 128u : (2 * block_n <= 256) ? 256u : 512u;
+  const int acc_cols = r3 ? 3 * block_n : 2 * block_n;
+  const uint32_t tmem_cols = acc_cols <= 64 ? 64u : acc_cols <= 128 ? 128u : acc_cols <= 256 ? 256u : 512u;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmDY);
@@ -68,16 +83,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tfull[i], 1);
-      mbar_init(&bars->tempty[i], 4);
+      mbar_init(&bars->tempty[i], 4 * CG);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, tmem_cols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(&bars->tmem_base, tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&bars->tmem_base, tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -87,31 +108,35 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   if (warp == 0) {
     // TMA producer: the whole warp walks the ring; lane 0 arms the barrier, lanes 0..nbox-1 each issue one box so
     // the 2 + block_n/64 loads of a stage are issued in parallel instead of back to back by one thread.
-    const int nbox = 2 + block_n / 64;
     int s = 0;
     uint32_t ph = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = first_unit; u < units; u += unit_stride) {
       const int split = u / tiles;
       int t = u % tiles;
       const int m_blk = t % m_blocks;
       t /= m_blocks;
       const int n_blk = t % n_blocks;
-      const int tap = t / n_blocks;
+      const int tap = (t / n_blocks) * tps;
       const int c_lo = chunk_lo(split), c_hi = chunk_lo(split + 1);
       // chunk -> (tb, th, tw) once per unit, then incremental (no integer divisions inside the ring loop)
       int tw = c_lo % g.ntw, th = (c_lo / g.ntw) % g.nth, tb = c_lo / (g.ntw * g.nth);
       for (int c = c_lo; c < c_hi; ++c) {
         mbar_wait(&bars->empty[s], ph ^ 1);
         uint8_t* sa = smem + s * stage_bytes;
-        if (lane == 0) mbar_expect_tx(&bars->full[s], stage_bytes);
+        if (lane == 0 && cta_rank == 0) mbar_expect_tx(&bars->full[s], CG * stage_tx);
         __syncwarp();
         if (lane < 2) {
           const int yw = tw * g.TW * g.dy_mul + g.dy_pw, yh = th * g.TH * g.dy_mul + g.dy_ph;
-          tma_load_4d(sa + lane * 8192, &tmDY, &bars->full[s], m_blk * 128 + lane * 64, yw, yh, tb * g.TB);
-        } else if (lane < nbox) {
+          const int co0 = (m_blk * CG + cta_rank) * 128 + lane * 64;
+          if (CG == 2) tma_load_4d_pair(sa + lane * 8192, &tmDY, &bars->full[s], co0, yw, yh, tb * g.TB);
+          else tma_load_4d(sa + lane * 8192, &tmDY, &bars->full[s], co0, yw, yh, tb * g.TB);
+        } else if (lane < 2 + nb_cta / 64) {
           const int j = lane - 2;
           const int xw = tw * g.TW * g.in_mul + g.dx[tap], xh = th * g.TH * g.in_mul + g.dy[tap];
-          tma_load_4d(sa + kWgABytes + j * 8192, &tmX, &bars->full[s], n_blk * block_n + j * 64, xw, xh, tb * g.TB);
+          const int ci0 = n_blk * block_n + cta_rank * nb_cta + j * 64;
+          const CUtensorMap* mx = r3 ? &tmX2 : &tmX;
+          if (CG == 2) tma_load_4d_pair(sa + kWgABytes + j * xslot, mx, &bars->full[s], ci0, xw, xh, tb * g.TB);
+          else tma_load_4d(sa + kWgABytes + j * xslot, mx, &bars->full[s], ci0, xw, xh, tb * g.TB);
         }
         if (++s == stages) { s = 0; ph ^= 1; }
         if (++tw == g.ntw) {
@@ -121,12 +146,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, block_n, true, true);
+    const uint32_t idesc = make_idesc_bf16(128 * CG, block_n, true, true);
     int s = 0;
     uint32_t ph = 0;
     int acc = 0;
     uint32_t pacc = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = first_unit; cta_rank == 0 && u < units; u += unit_stride) {
       const int split = u / tiles;
       const int nk = chunk_lo(split + 1) - chunk_lo(split);
       if (nk == 0) continue;
@@ -138,28 +163,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
-          // MN-major, 128B swizzle: LBO = 8192 (next 64-channel atom), SBO = 1024 (next 8-pixel group)
+          // MN-major, 128B swizzle: LBO = distance to the next 64-channel atom, SBO = 1024 (next 8-pixel group)
           const uint64_t adesc = make_smem_desc_sw128(sa, 8192, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + kWgABytes, 8192, 1024);
+          for (int j = 0; j < tps; ++j) {
+            // tap j of the filter row: same X box, start shifted by j pixel rows (128 B each); the swizzle is a
+            // function of absolute smem address bits, so the shifted start needs no base_offset
+            const uint64_t bdesc = make_smem_desc_sw128(sa + kWgABytes + j * 128, xslot, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 16 pixels = 16 rows of 128 B = 2048 B -> +128 in the (addr>>4) field
-            umma_bf16(tmem_d, adesc + 128 * k, bdesc + 128 * k, idesc, (ks | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              // advance 16 pixels = 16 rows of 128 B = 2048 B -> +128 in the (addr>>4) field
+              if (CG == 2) umma_bf16_pair(tmem_d + j * block_n, adesc + 128 * k, bdesc + 128 * k, idesc, (ks | k) != 0);
+              else umma_bf16(tmem_d + j * block_n, adesc + 128 * k, bdesc + 128 * k, idesc, (ks | k) != 0);
+            }
           }
-          umma_commit(&bars->empty[s]);
-          if (ks == nk - 1) umma_commit(&bars->tfull[acc]);
+          if (CG == 2) {
+            umma_commit_pair(&bars->empty[s]);
+            if (ks == nk - 1) umma_commit_pair(&bars->tfull[acc]);
+          } else {
+            umma_commit(&bars->empty[s]);
+            if (ks == nk - 1) umma_commit(&bars->tfull[acc]);
+          }
         }
         __syncwarp();
         if (++s == stages) { s = 0; ph ^= 1; }
       }
-      if (++acc == 2) { acc = 0; pacc ^= 1; }
+      if (++acc == nacc) { acc = 0; pacc ^= 1; }
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t pacc = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = first_unit; u < units; u += unit_stride) {
       const int split = u / tiles;
       const int nk = chunk_lo(split + 1) - chunk_lo(split);
       if (nk == 0) continue;
@@ -167,38 +202,45 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const int m_blk = t % m_blocks;
       t /= m_blocks;
       const int n_blk = t % n_blocks;
-      const int tap = t / n_blocks;
-      const int co = m_blk * 128 + row;
-      float* dst_row = dw + (static_cast<size_t>(g.slab[tap]) * g.Cout + co) * g.Cin + n_blk * block_n;
+      const int tap0 = (t / n_blocks) * tps;
+      const int co = (m_blk * CG + cta_rank) * 128 + row;
       mbar_wait(&bars->tfull[acc], pacc);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * block_n;
-      for (int c0 = 0; c0 < block_n; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        tmem_ld_wait();
-        if (co < g.Cout) {
+      for (int j = 0; j < tps; ++j) {
+        float* dst_row = dw + (static_cast<size_t>(g.slab[tap0 + j]) * g.Cout + co) * g.Cin + n_blk * block_n;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc + j) * block_n;
+        for (int c0 = 0; c0 < block_n; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          if (co < g.Cout) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int ci = n_blk * block_n + c0 + 4 * j;
-            if (ci < g.Cin)
-              red_add_v4(dst_row + c0 + 4 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            for (int jj = 0; jj < 8; ++jj) {
+              const int ci = n_blk * block_n + c0 + 4 * jj;
+              if (ci < g.Cin)
+                red_add_v4(dst_row + c0 + 4 * jj, __uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
+                           __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tempty[acc]);
-      if (++acc == 2) { acc = 0; pacc ^= 1; }
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(&bars->tempty[acc], 0);
+        else mbar_arrive(&bars->tempty[acc]);
+      }
+      if (++acc == nacc) { acc = 0; pacc ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -212,16 +254,47 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
   g.nth = g.GH / g.TH;
   g.ntb = (g.GB + g.TB - 1) / g.TB;
   int bn = g.Cin >= 256 ? 256 : g.Cin >= 128 ? 128 : 64;
+  // sort taps by (dy, dx); runs of three with equal dy and consecutive dx can share one X box (reuse3)
+  for (int i = 1; i < g.ntaps; ++i)
+    for (int j = i; j > 0 && (g.dy[j] < g.dy[j - 1] || (g.dy[j] == g.dy[j - 1] && g.dx[j] < g.dx[j - 1])); --j) {
+      int t;
+      t = g.dy[j]; g.dy[j] = g.dy[j - 1]; g.dy[j - 1] = t;
+      t = g.dx[j]; g.dx[j] = g.dx[j - 1]; g.dx[j - 1] = t;
+      t = g.slab[j]; g.slab[j] = g.slab[j - 1]; g.slab[j - 1] = t;
+    }
+  static int reuse_mode = -1;
+  if (reuse_mode < 0) {
+    const char* e = getenv("LUN_WGRAD_REUSE");
+    reuse_mode = e ? atoi(e) : 1;
+  }
+  bool r3 = reuse_mode && g.ntaps % 3 == 0 && g.TW == 64 && g.TH == 1 && g.TB == 1 && g.in_mul == 1 &&
+            g.dy_mul == 1 && g.Cin == 128;   // wider Cin: 256-column tiles in CTA-pair mode are faster (less smem reads per MMA)
+  for (int i = 0; r3 && i < g.ntaps; i += 3)
+    r3 = g.dy[i + 1] == g.dy[i] && g.dy[i + 2] == g.dy[i] && g.dx[i + 1] == g.dx[i] + 1 && g.dx[i + 2] == g.dx[i] + 2;
+  g.reuse3 = r3 ? 1 : 0;
+  if (r3) bn = 128;                 // three 128-column accumulators (384 TMEM columns, single set)
   g.block_n = bn;
   if (g.TW * g.in_mul > 256 || g.TH * g.in_mul > 256 || g.TW * g.dy_mul > 256 || g.TH * g.dy_mul > 256) return 5;
 
-  CUtensorMap tmDY, tmX;
+  CUtensorMap tmDY, tmX, tmX2;
   int rc = make_tmap_nhwc(&tmDY, dy, YB, YH, YW, g.Cout, g.TW * g.dy_mul, g.TH * g.dy_mul, g.TB, g.dy_mul);
   if (rc) return rc;
   rc = make_tmap_nhwc(&tmX, x, XB, XH, XW, g.Cin, g.TW * g.in_mul, g.TH * g.in_mul, g.TB, g.in_mul);
   if (rc) return rc;
+  if (r3) {
+    rc = make_tmap_nhwc(&tmX2, x, XB, XH, XW, g.Cin, g.TW + 2, 1, 1, 1);
+    if (rc) return rc;
+  } else {
+    tmX2 = tmX;
+  }
 
-  const int stage_bytes = kWgABytes + bn * 128;
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char* e = getenv("LUN_WGRAD_PAIR");
+    pair_mode = e ? atoi(e) : 1;
+  }
+  const int cg = (pair_mode && !r3 && bn == 256 && g.Cout % 256 == 0 && g.Cin % 256 == 0 && num_sms() % 2 == 0) ? 2 : 1;
+  const int stage_bytes = kWgABytes + bn / cg / 64 * (r3 ? kWgXSlot : 8192);
   const int extra = (int)sizeof(WgBars) + 1024;
   int stages = (227 * 1024 - extra) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -229,27 +302,47 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
   const int smem_bytes = stages * stage_bytes + extra;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess)
       return 8;
     configured = true;
   }
-  const int m_blocks = (g.Cout + 127) / 128, n_blocks = (g.Cin + bn - 1) / bn;
-  const int tiles = m_blocks * n_blocks * g.ntaps;
+  const int m_blocks = (g.Cout + 128 * cg - 1) / (128 * cg), n_blocks = (g.Cin + bn - 1) / bn;
+  const int tiles = m_blocks * n_blocks * (g.ntaps / (r3 ? 3 : 1));
   const int chunks = g.ntb * g.nth * g.ntw;
   // K-splits: make the unit count a multiple of the SM count when the reduction is long enough (perfect balance of
   // the persistent grid), otherwise ~4 units per SM; keep at least 8 k-chunks per unit
-  int a = tiles, b = num_sms();
+  const int workers = num_sms() / cg;               // CTAs (or CTA pairs) that walk the unit list
+  int a = tiles, b = workers;
   while (b) { const int r = a % b; a = b; b = r; }
-  int splits = num_sms() / a;                       // tiles * splits == lcm(tiles, SMs)
-  while (splits * tiles < 4 * num_sms()) splits *= 2;
-  if (splits > chunks / 8) splits = (4 * num_sms() + tiles - 1) / tiles;
+  int splits = workers / a;                         // tiles * splits == lcm(tiles, workers)
+  while (splits * tiles < 4 * workers) splits *= 2;
+  if (splits > chunks / 8) splits = (4 * workers + tiles - 1) / tiles;
   if (splits > chunks / 8) splits = chunks / 8;
   if (splits < 1) splits = 1;
   g.splits = splits;
-  int grid = num_sms();
+  int grid = workers;
   if (grid > tiles * splits) grid = tiles * splits;
-  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, g, dw);
+  grid *= cg;
+  if (cg == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<2>, tmDY, tmX, tmX2, g, dw) != cudaSuccess) return 9;
+  } else {
+    conv_wgrad_kernel<1><<<grid, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, tmX2, g, dw);
+  }
   note_launch(1);
   return cudaGetLastError() == cudaSuccess ? 0 : 9;
 }

@@ -28,26 +28,33 @@ __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
 }
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// splitmix64: counter-based, stateless. One call yields four 16-bit uniforms.
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
+// Counter-based, stateless dropout RNG: a 32-bit integer hash (lowbias32) of (seed, element index); one hash yields
+// two 16-bit uniforms. The same function regenerates the mask in the backward pass.
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(uint64_t seed, uint64_t idx8) {
+  return static_cast<uint32_t>(seed) ^ (static_cast<uint32_t>(idx8) * 4u) ^
+         (static_cast<uint32_t>(idx8 >> 30) * 0x9E3779B9U) ^ static_cast<uint32_t>(seed >> 32) * 0x85EBCA6BU;
 }
 // keep[i] for elements 8*idx8 .. 8*idx8+7 of a logical tensor; element is dropped when its 16-bit uniform < thresh16.
 __device__ __forceinline__ void drop_keep8(uint64_t seed, uint64_t idx8, uint32_t thresh16, bool (&keep)[8]) {
-  const uint64_t a = splitmix64(seed ^ (idx8 * 2));
-  const uint64_t b = splitmix64(seed ^ (idx8 * 2 + 1));
+  const uint32_t k = drop_key(seed, idx8);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    keep[i] = ((a >> (16 * i)) & 0xFFFF) >= thresh16;
-    keep[4 + i] = ((b >> (16 * i)) & 0xFFFF) >= thresh16;
+    const uint32_t h = hash32(k + i);
+    keep[2 * i] = (h & 0xFFFFu) >= thresh16;
+    keep[2 * i + 1] = (h >> 16) >= thresh16;
   }
 }
 __device__ __forceinline__ bool drop_keep1(uint64_t seed, uint64_t idx, uint32_t thresh16) {
-  const uint64_t a = splitmix64(seed ^ ((idx >> 3) * 2 + ((idx >> 2) & 1)));
-  return ((a >> (16 * (idx & 3))) & 0xFFFF) >= thresh16;
+  const uint32_t h = hash32(drop_key(seed, idx >> 3) + ((idx >> 1) & 3));
+  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thresh16;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
