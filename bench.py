@@ -275,7 +275,7 @@ def main():
     p.add_argument("--latent", type=int, default=CFG["latent"])
     p.add_argument("--emb", type=int, default=CFG["emb"])
     p.add_argument("--feat", type=int, default=CFG["feat"])
-    p.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=1)
+    p.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4)
     p.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     a = p.parse_args()
     if a.impl == "reference":

@@ -192,6 +192,13 @@ int lun_vae_loss_bwd(const float* recon, const float* images, const float* mulv,
  * in [-1,1], x/127.5 - 1 (PixelArtDataset.__getitem__, train_hybrid.py:181-182). */
 int lun_sprites_u8_to_f32(const void* u8_nhwc, float* out_nchw, int B, int H, int W, void* stream);
 
+/* SelfAttention2d (lunar_generate.py:56-78) as a flash-style tcgen05 kernel: y = gamma * softmax(q k^T) v + x over
+ * all N = H*W positions of each image, no N x N matrix. qk: [B*N, 128] bf16 rows = [q | k], each zero-padded from
+ * C/8 to 64 columns (the 1x1 query / key convs write it); v, x, y: [B, N, C] bf16; gamma: device scalar.
+ * N % 128 == 0, C % 64 == 0, C/8 <= 64. */
+int lun_flash_attn2d_bf16(const void* qk, const void* v, const void* x, void* y, const float* gamma, int B, int N,
+                          int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,7 @@ SIGNATURES = {
     "lun_vae_loss_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p],
     "lun_vae_loss_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p],
     "lun_sprites_u8_to_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "lun_flash_attn2d_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "lun_fe_branches": [c_void_p, c_void_p, c_void_p, c_pp, c_pp, c_pp, c_pp, c_void_p, c_int, c_int, c_int, c_float,
                         c_void_p],
 }

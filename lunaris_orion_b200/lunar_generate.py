@@ -47,8 +47,41 @@ class SelfAttention2d(nn.Module):
         self.gamma = nn.Parameter(torch.zeros(1))
 
     def forward(self, x):
-        raise _capi.LunarisB200Error("SelfAttention2d is not on the train_hybrid path (never instantiated by the "
-                                     "reference); its global-attention kernel is not built yet")
+        """y = gamma * softmax(q^T k) v + x (lunar_generate.py:66-78) through the flash-style tcgen05 kernel
+        (csrc/flash_attn2d_sm100.cu). Forward only: the reference never instantiates this class, and its backward
+        kernel is not built - a call that needs gradients raises instead of silently detaching."""
+        if not x.is_cuda:
+            raise _capi.LunarisB200Error("lunaris_orion_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise _capi.LunarisB200Error("SelfAttention2d backward is not implemented (forward / inference only)")
+        B, C, H, W = x.shape
+        N, dq = H * W, C // 8
+        if N % 128 or C % 64 or dq > 64:
+            raise _capi.LunarisB200Error("SelfAttention2d kernel needs H*W % 128 == 0, C % 64 == 0, C <= 512")
+        xf = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).view(B * N, C)
+
+        def build_qk():
+            w = torch.zeros(128, C, device=x.device)
+            w[:dq] = self.query_conv.weight.detach().view(dq, C)
+            w[64:64 + dq] = self.key_conv.weight.detach().view(dq, C)
+            return w.to(torch.bfloat16).contiguous()
+
+        def build_qk_bias():
+            bq = torch.zeros(128, device=x.device)
+            bq[:dq] = self.query_conv.bias.detach()
+            bq[64:64 + dq] = self.key_conv.bias.detach()
+            return bq.contiguous()
+        wqk = _cached((self.query_conv.weight, self.key_conv.weight), "sa_qk", build_qk)
+        bqk = _cached((self.query_conv.bias, self.key_conv.bias), "sa_qk_bias", build_qk_bias)
+        wv = _cached((self.value_conv.weight,), "sa_v", lambda: self.value_conv.weight.detach().view(C, C)
+                     .to(torch.bfloat16).contiguous())
+        qk = ops.linear_fprop(xf, wqk, bqk, out_f32=False)                       # [B*N, 128] = [q | k], zero padded
+        v = ops.linear_fprop(xf, wv, _f32(self.value_conv.bias), out_f32=False)  # [B*N, C]
+        y = torch.empty(B, N, C, device=x.device, dtype=torch.bfloat16)
+        check(_capi.lib().lun_flash_attn2d_bf16(qk.data_ptr(), v.data_ptr(), xf.data_ptr(), y.data_ptr(),
+                                                _f32(self.gamma).data_ptr(), B, N, C, _stream()),
+              "lun_flash_attn2d_bf16")
+        return y.view(B, H, W, C).permute(0, 3, 1, 2).float()
 
 
 class Encoder(nn.Module):

@@ -43,3 +43,36 @@ def test_fused_losses_and_sprite_loader_match_torch(cuda_dev):
     u8 = torch.randint(0, 256, (3, 128, 128, 3), generator=g, dtype=torch.uint8).to(cuda_dev)
     # the reference normalises on the CPU inside PixelArtDataset (true division); compare with that, bit for bit
     assert torch.equal(sprites_to_tensor(u8).cpu(), u8.cpu().permute(0, 3, 1, 2).float() / 127.5 - 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,HW", [(64, 16), (256, 32), (512, 16)])
+def test_self_attention2d_flash_kernel_matches_reference_math(cuda_dev, C, HW):
+    """SelfAttention2d.forward (flash-style tcgen05 kernel) vs the reference formula of lunar_generate.py:66-78 in
+    fp32 on bf16-rounded operands. Tolerance: 2 % of max |ref| (bf16 q/k/v/P, fp32 accumulation)."""
+    import torch
+    import torch.nn.functional as F
+    from lunaris_orion_b200 import lunar_generate as lg
+    torch.manual_seed(C + HW)
+    att = lg.SelfAttention2d(C).to(cuda_dev)
+    with torch.no_grad():
+        att.gamma.fill_(0.7)
+        for m in (att.query_conv, att.key_conv):
+            m.weight.mul_(0.5)
+    x = torch.randn(2, C, HW, HW, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        mine = att(x.to(cuda_dev)).cpu()
+        w = {k: v.detach().cpu().float() for k, v in att.state_dict().items()}
+        bf = lambda t: t.to(torch.bfloat16).float()
+        xb = bf(x)
+        B, N = 2, HW * HW
+        q = bf(F.conv2d(xb, bf(w["query_conv.weight"]), w["query_conv.bias"])).view(B, -1, N)
+        k = bf(F.conv2d(xb, bf(w["key_conv.weight"]), w["key_conv.bias"])).view(B, -1, N)
+        v = bf(F.conv2d(xb, bf(w["value_conv.weight"]), w["value_conv.bias"])).view(B, -1, N)
+        attn = torch.softmax(torch.bmm(q.permute(0, 2, 1), k), dim=-1)
+        out = torch.bmm(v, attn.permute(0, 2, 1)).view(B, C, HW, HW)
+        ref = w["gamma"] * out + xb
+    err = (mine - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-2, err
+    with pytest.raises(Exception):
+        att(x.to(cuda_dev).requires_grad_(True))
