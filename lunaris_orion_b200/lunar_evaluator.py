@@ -371,11 +371,16 @@ def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save):
     p_proj = att.proj_drop.p if training else 0.0
     att._touch_rel_pos(H, W, y1.device)
     mq, cq, wv_bd, bv = _folded_attention_weights(att)
-    xq = torch.zeros(B, nq_pad, C, device=y1.device, dtype=torch.bfloat16)
+    xq = torch.empty(B, nq_pad, C, device=y1.device, dtype=torch.bfloat16)
+    if nq_pad > nq:
+        xq[:, nq:].zero_()                       # only the padding rows need defined contents
     check(lib.lun_gather_query_rows_affine_bf16(y1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), _p(m1), xq.data_ptr(),
                                                 B, HW, C, nq_pad, _stream()), "lun_gather_query_rows_affine_bf16")
     qt = ops.linear_fprop(xq.view(B * nq_pad, C), mq, cq, out_f32=False)              # [B*nq_pad, heads*C]
-    xbar = torch.zeros(B * nq_pad, heads * C, device=y1.device, dtype=torch.bfloat16)
+    xbar = torch.empty(B, nq_pad, heads * C, device=y1.device, dtype=torch.bfloat16)
+    if nq_pad > nq:
+        xbar[:, nq:].zero_()
+    xbar = xbar.view(B * nq_pad, heads * C)
     check(lib.lun_attn_fold_rows_bf16(y1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), _p(m1), qt.data_ptr(),
                                       xbar.data_ptr(), B, HW, C, heads, nq_pad, _cpu_seed() if p_attn > 0 else 0,
                                       float(p_attn), _stream()), "lun_attn_fold_rows_bf16")
