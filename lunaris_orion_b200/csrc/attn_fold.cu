@@ -15,6 +15,7 @@
 #include "elem_common.cuh"
 #include "ptx.cuh"
 #include "launch_count.cuh"
+#include <stdlib.h>
 
 namespace lun {
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   y     [B, N, C]        attention input BEFORE BatchNorm (conv1 output)
 //   qt    [B, nq_pad, 8*C] folded queries (head-major)
 //   xbar  [B, nq_pad, 8*C] output
-template <int C>
+template <int C, int NBUF>
 __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                                                                const float* __restrict__ shift,
                                                                const float* __restrict__ m2,
@@ -74,14 +75,16 @@ __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __res
   static_assert(kAfThreads % CH8 == 0 && NL >= 1, "unsupported channel count");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* Xs0 = reinterpret_cast<bf16*>(smem_raw);            // [2][32][PITCH] raw chunk rows (tokens), double buffer
-  bf16* Qs = Xs0 + 2 * 32 * PITCH;                          // [8][PITCH] scaled queries
-  float* Sp = reinterpret_cast<float*>(Qs + 8 * PITCH);     // [4 warps][8][32] partial scores
+  bf16* Qs = Xs0 + NBUF * 32 * PITCH;                       // [8][PITCH] scaled queries
+  float* Sp = reinterpret_cast<float*>(Qs + 8 * PITCH);     // [8 warps][8][32] partial scores
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nc = N / 32;
   const int items = B * nq;
   const int c8 = tid % CH8, r0 = tid / CH8;
   const int g = lane >> 2, t4 = lane & 3;
-  constexpr int KW = C / 4;                        // channels per warp
+  constexpr int NWARPS = kAfThreads / 32;
+  constexpr int NW = (C / 16 < NWARPS) ? C / 16 : NWARPS;   // warps that take part in the two contractions
+  constexpr int KW = C / NW;                       // channels per warp
 
   auto issue_chunk = [&](int item, int buf) {
     const int b = item / nq, i = item % nq;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __res
     load_q(item, qraw, mraw);
   }
   int buf = 0;
-  for (; item < items; item += gridDim.x, buf ^= 1) {
+  for (; item < items; item += gridDim.x, buf ^= (NBUF - 1)) {
     const int b = item / nq, i = item % nq;
     // stage this item's queries scaled by m*s, then prefetch the next item's
 #pragma unroll
@@ -146,10 +149,10 @@ __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __res
     }
     const int next = item + gridDim.x;
     if (next < items) {
-      issue_chunk(next, buf ^ 1);
+      if (NBUF == 2) issue_chunk(next, buf ^ 1);
       load_q(next, qraw, mraw);
     }
-    if (next < items) cp_async_wait<1>(); else cp_async_wait<0>();   // this item's chunk has landed
+    if (NBUF == 2 && next < items) cp_async_wait<1>(); else cp_async_wait<0>();   // this item's chunk has landed
     __syncthreads();
 
     // ---- S = Q' Y^T : each warp owns a quarter of the channel (k) range, partials are summed through smem
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __res
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[n][e] = 0.f;
 #pragma unroll 2
-    for (int k0 = warp * KW; k0 < (warp + 1) * KW; k0 += 16) {
+    for (int k0 = warp * KW; warp < NW && k0 < (warp + 1) * KW; k0 += 16) {
       uint32_t a[4], a2[2];
       ldsm_x2(a2, qs_base + ((lane & 7) * PITCH + k0 + ((lane >> 3) & 1) * 8) * 2);
       a[0] = a2[0]; a[1] = 0u; a[2] = a2[1]; a[3] = 0u;          // rows 8..15 of the M=16 tile are padding
@@ -171,11 +174,13 @@ __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __res
         mma_bf16_16816(s[n], a, bb);
       }
     }
+    if (warp < NW) {
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      float* sp = Sp + (warp * 8 + g) * 32 + n * 8 + t4 * 2;
-      sp[0] = s[n][0];
-      sp[1] = s[n][1];
+      for (int n = 0; n < 4; ++n) {
+        float* sp = Sp + (warp * 8 + g) * 32 + n * 8 + t4 * 2;
+        sp[0] = s[n][0];
+        sp[1] = s[n][1];
+      }
     }
     __syncthreads();
     // every warp rebuilds the full score fragment (rows = heads g, cols = tokens)
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __res
       s[n][1] = 0.f;
     }
 #pragma unroll
-    for (int w = 0; w < 4; ++w)
+    for (int w = 0; w < NW; ++w)
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         const float2 t = *reinterpret_cast<const float2*>(Sp + (w * 8 + g) * 32 + n * 8 + t4 * 2);
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __res
     // ---- Ybar = P Y, then xbar = m*(s*Ybar + t*psum); each warp owns a quarter of the output channels
     bf16* out = xbar + (((size_t)b * nq_pad + i) * 8 + g) * C;
 #pragma unroll 4
-    for (int n0 = warp * KW; n0 < (warp + 1) * KW; n0 += 8) {
+    for (int n0 = warp * KW; warp < NW && n0 < (warp + 1) * KW; n0 += 8) {
       float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __res
       *reinterpret_cast<uint32_t*>(out + c) = pack2(mk.x * (sc.x * d[0] + sh.x * psum), mk.y * (sc.y * d[1] + sh.y * psum));
     }
     __syncthreads();                               // Qs / Sp / this X buffer are rewritten by the next iterations
+    if (NBUF == 1 && next < items) issue_chunk(next, 0);
   }
 }
 
@@ -276,20 +282,32 @@ template <int C>
 static int launch_fold(const bf16* y, const float* scale, const float* shift, const float* m2, const bf16* qt,
                        bf16* xbar, int B, int N, int nq, int nq_pad, unsigned long long seed, unsigned int th,
                        float ds, cudaStream_t st) {
-  const int smem = (64 + 8) * (C + 8) * 2 + 4 * 8 * 32 * 4;
+  static int nbuf = 0;
+  if (!nbuf) {
+    const char* e = getenv("LUN_ATTN_NBUF");
+    nbuf = e ? atoi(e) : 1;
+    if (nbuf != 2) nbuf = 1;
+  }
+  const int smem = (32 * nbuf + 8) * (C + 8) * 2 + 8 * 8 * 32 * 4;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fold_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fold_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_fold_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
       return LUN_E_ATTR;
     configured = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int per_sm = (220 * 1024) / smem > 0 ? (220 * 1024) / smem : 1;
-  int grid = sms * (per_sm > 4 ? 4 : per_sm);
+  int per_sm = (224 * 1024) / (smem + 1024);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int grid = sms * per_sm;
   if (grid > B * nq) grid = B * nq;
-  attn_fold_kernel<C><<<grid, kAfThreads, smem, st>>>(y, scale, shift, m2, qt, xbar, B, N, nq, nq_pad, seed, th, ds);
+  if (nbuf == 2)
+    attn_fold_kernel<C, 2><<<grid, kAfThreads, smem, st>>>(y, scale, shift, m2, qt, xbar, B, N, nq, nq_pad, seed, th, ds);
+  else
+    attn_fold_kernel<C, 1><<<grid, kAfThreads, smem, st>>>(y, scale, shift, m2, qt, xbar, B, N, nq, nq_pad, seed, th, ds);
   return LUN_OK;
 }
 
