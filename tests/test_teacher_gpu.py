@@ -139,3 +139,12 @@ def test_folded_attention_module_matches_oracle(cuda_dev):
     nq = 64 * 64 // 32 + 31
     flat = mine.permute(0, 2, 3, 1).reshape(2, -1, 128)
     assert torch.allclose(flat[:, nq:], w["proj.bias"].to(torch.bfloat16).float().expand_as(flat[:, nq:]))
+
+
+@pytest.mark.gpu
+def test_teacher_trunk_feat256_config2_shapes(cuda_dev):
+    """Same trunk parity at feature_dim 256 (BASELINE configs[1], head_dim 32, single 256-wide N block)."""
+    rep = tc.trunk_report(cuda_dev, B=2, feat=256, calibrate=True)
+    assert rep["grad_keys_equal"]
+    assert rep["pool"] <= 3 * rep["cal_pool"] + 2e-3
+    assert rep["grad_rel_max"] <= 3 * rep["cal_grad_rel_max"] + 0.02, rep["grad_worst"]
