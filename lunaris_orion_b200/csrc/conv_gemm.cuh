@@ -53,6 +53,7 @@ struct WgradGeom {
   int dy_mul, dy_ph, dy_pw;  // dY pixel = grid*dy_mul + phase  (transposed-conv phases)
   // reuse3: the three dx taps of a filter row share one (TW+2)-pixel X box; a unit accumulates 3 tiles (one per tap)
   int reuse3;
+  int kpx;   // pixels (GEMM-K rows) per pipeline stage: 64, or 128 in CTA-pair mode (halves the per-stage issue overhead)
 };
 
 }  // namespace lun

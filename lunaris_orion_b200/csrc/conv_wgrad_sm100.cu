@@ -51,12 +51,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int block_n = g.block_n;
   const bool r3 = g.reuse3 != 0;
-  const int xslot = r3 ? kWgXSlot : 8192;                 // bytes between the 64-channel atoms of the X operand
+  const int atom = g.kpx * 128;                           // bytes of one 64-channel atom: kpx pixel rows x 128 B
+  const int a_bytes = 2 * atom;                           // dY operand: 128 Cout columns
+  const int xslot = r3 ? kWgXSlot : atom;                 // bytes between the 64-channel atoms of the X operand
   const int nb_cta = block_n / CG;                        // Cin columns of the X operand loaded by this CTA
   const int b_bytes = nb_cta / 64 * xslot;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
-  const int stage_bytes = kWgABytes + b_bytes;
-  const int stage_tx = kWgABytes + nb_cta / 64 * (r3 ? kWgXBox : 8192);
+  const int stage_bytes = a_bytes + b_bytes;
+  const int stage_tx = a_bytes + nb_cta / 64 * (r3 ? kWgXBox : atom);
   const int tps = r3 ? 3 : 1;                             // taps accumulated per unit
   const int nacc = r3 ? 1 : 2;                            // accumulator sets in TMEM
   const int stages = g.stages;
@@ -128,15 +130,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         if (lane < 2) {
           const int yw = tw * g.TW * g.dy_mul + g.dy_pw, yh = th * g.TH * g.dy_mul + g.dy_ph;
           const int co0 = (m_blk * CG + cta_rank) * 128 + lane * 64;
-          if (CG == 2) tma_load_4d_pair(sa + lane * 8192, &tmDY, &bars->full[s], co0, yw, yh, tb * g.TB);
-          else tma_load_4d(sa + lane * 8192, &tmDY, &bars->full[s], co0, yw, yh, tb * g.TB);
+          if (CG == 2) tma_load_4d_pair(sa + lane * atom, &tmDY, &bars->full[s], co0, yw, yh, tb * g.TB);
+          else tma_load_4d(sa + lane * atom, &tmDY, &bars->full[s], co0, yw, yh, tb * g.TB);
         } else if (lane < 2 + nb_cta / 64) {
           const int j = lane - 2;
           const int xw = tw * g.TW * g.in_mul + g.dx[tap], xh = th * g.TH * g.in_mul + g.dy[tap];
           const int ci0 = n_blk * block_n + cta_rank * nb_cta + j * 64;
           const CUtensorMap* mx = r3 ? &tmX2 : &tmX;
-          if (CG == 2) tma_load_4d_pair(sa + kWgABytes + j * xslot, mx, &bars->full[s], ci0, xw, xh, tb * g.TB);
-          else tma_load_4d(sa + kWgABytes + j * xslot, mx, &bars->full[s], ci0, xw, xh, tb * g.TB);
+          if (CG == 2) tma_load_4d_pair(sa + a_bytes + j * xslot, mx, &bars->full[s], ci0, xw, xh, tb * g.TB);
+          else tma_load_4d(sa + a_bytes + j * xslot, mx, &bars->full[s], ci0, xw, xh, tb * g.TB);
         }
         if (++s == stages) { s = 0; ph ^= 1; }
         if (++tw == g.ntw) {
@@ -164,13 +166,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
           // MN-major, 128B swizzle: LBO = distance to the next 64-channel atom, SBO = 1024 (next 8-pixel group)
-          const uint64_t adesc = make_smem_desc_sw128(sa, 8192, 1024);
+          const uint64_t adesc = make_smem_desc_sw128(sa, atom, 1024);
+          const int nkk = g.kpx >> 4;              // K=16 pixel MMAs per stage
           for (int j = 0; j < tps; ++j) {
             // tap j of the filter row: same X box, start shifted by j pixel rows (128 B each); the swizzle is a
             // function of absolute smem address bits, so the shifted start needs no base_offset
-            const uint64_t bdesc = make_smem_desc_sw128(sa + kWgABytes + j * 128, xslot, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            const uint64_t bdesc = make_smem_desc_sw128(sa + a_bytes + j * 128, xslot, 1024);
+#pragma unroll 4
+            for (int k = 0; k < nkk; ++k) {
               // advance 16 pixels = 16 rows of 128 B = 2048 B -> +128 in the (addr>>4) field
               if (CG == 2) umma_bf16_pair(tmem_d + j * block_n, adesc + 128 * k, bdesc + 128 * k, idesc, (ks | k) != 0);
               else umma_bf16(tmem_d + j * block_n, adesc + 128 * k, bdesc + 128 * k, idesc, (ks | k) != 0);
@@ -249,7 +252,9 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
                       float* dw, cudaStream_t stream) {
   if (g.ntaps < 1 || g.ntaps > kMaxTaps) return 3;
   if (g.Cin % 4 != 0 || g.Cout % 8 != 0 || g.Cin % 8 != 0) return 2;
+  // first pass with 64-pixel K chunks to decide the mode; CTA-pair mode re-tiles with 128-pixel chunks below
   if (!tile_grid(g.GB, g.GH, g.GW, 64, &g.TB, &g.TH, &g.TW)) return 4;
+  g.kpx = 64;
   g.ntw = g.GW / g.TW;
   g.nth = g.GH / g.TH;
   g.ntb = (g.GB + g.TB - 1) / g.TB;
@@ -294,7 +299,27 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
     pair_mode = e ? atoi(e) : 1;
   }
   const int cg = (pair_mode && !r3 && bn == 256 && g.Cout % 256 == 0 && g.Cin % 256 == 0 && num_sms() % 2 == 0) ? 2 : 1;
-  const int stage_bytes = kWgABytes + bn / cg / 64 * (r3 ? kWgXSlot : 8192);
+  static int kpx_mode = -1;
+  if (kpx_mode < 0) {
+    const char* e = getenv("LUN_WGRAD_KPX");
+    kpx_mode = e ? atoi(e) : 128;
+  }
+  if (cg == 2 && kpx_mode == 128 && (long)g.GB * g.GH * g.GW % 128 == 0 && g.GW * g.GH >= 128) {
+    int tb, th, tw;
+    if (tile_grid(g.GB, g.GH, g.GW, 128, &tb, &th, &tw) && tb == 1 && tw * g.in_mul <= 256 && tw * g.dy_mul <= 256) {
+      g.kpx = 128;
+      g.TB = tb; g.TH = th; g.TW = tw;
+      g.ntw = g.GW / g.TW;
+      g.nth = g.GH / g.TH;
+      g.ntb = (g.GB + g.TB - 1) / g.TB;
+      rc = make_tmap_nhwc(&tmDY, dy, YB, YH, YW, g.Cout, g.TW * g.dy_mul, g.TH * g.dy_mul, g.TB, g.dy_mul);
+      if (rc) return rc;
+      rc = make_tmap_nhwc(&tmX, x, XB, XH, XW, g.Cin, g.TW * g.in_mul, g.TH * g.in_mul, g.TB, g.in_mul);
+      if (rc) return rc;
+      tmX2 = tmX;
+    }
+  }
+  const int stage_bytes = 2 * g.kpx * 128 + bn / cg / 64 * (r3 ? kWgXSlot : g.kpx * 128);
   const int extra = (int)sizeof(WgBars) + 1024;
   int stages = (227 * 1024 - extra) / stage_bytes;
   if (stages > 8) stages = 8;
