@@ -335,21 +335,21 @@ __global__ void __launch_bounds__(kEThreads, 3) blk_bwd_apply_kernel(const BlkBw
   extern __shared__ __align__(16) float smem[];
   const ChanGeom g(a.C);
   const int C = a.C;
-  float* sP = smem;                       // [7][C]: mean, rstd, gm, s1, s2, k0, gpool
-  float* sRed = smem + 7 * C;             // [lanes][C]
+  float* sP = smem;                       // [4][C]: P1, P2, P3 (dz = P1*d + P2*a + P3), gpool
+  float* sRed = smem + 4 * C;             // [lanes][C]
   const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
   const bool active = lane_px < g.lanes;
   const int b = blockIdx.y, c0 = cgi * 8;
   for (int c = threadIdx.x; c < C; c += kEThreads) {
+    // dz = gamma*rstd * (g - S1/n - xhat*S2/n),  g = d*ls*m2,  xhat = (a - mean)*rstd
     const float ls = a.ls ? a.ls[c] : 1.f;
-    const float rstd = a.rstd[c];
-    sP[c] = a.mean[c];
-    sP[C + c] = rstd;
-    sP[2 * C + c] = ls * (a.m2 ? a.m2[(size_t)b * C + c] : 1.f);   // g = dpre * gm
-    sP[3 * C + c] = ls * a.t1[c] * a.inv_n;
-    sP[4 * C + c] = ls * a.t2[c] * a.inv_n;
-    sP[5 * C + c] = a.gamma[c] * rstd;
-    sP[6 * C + c] = a.gpool ? a.gpool[(size_t)b * C + c] : 0.f;
+    const float rstd = a.rstd[c], mean = a.mean[c];
+    const float k0 = a.gamma[c] * rstd;
+    const float s1 = ls * a.t1[c] * a.inv_n, s2 = ls * a.t2[c] * a.inv_n;
+    sP[c] = k0 * ls * (a.m2 ? a.m2[(size_t)b * C + c] : 1.f);
+    sP[C + c] = -k0 * s2 * rstd;
+    sP[2 * C + c] = k0 * (s2 * rstd * mean - s1);
+    sP[3 * C + c] = a.gpool ? a.gpool[(size_t)b * C + c] : 0.f;
   }
   __syncthreads();
   float acc[1][8] = {};
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kEThreads, 3) blk_bwd_apply_kernel(const BlkBw
         float d[8], av[8], t0[8], t1[8];
         if (a.dpre) unpack8(dr[u], d);
         else {
-          lds8(sP + 6 * C + c0, d);
+          lds8(sP + 3 * C + c0, d);
           if (a.out) {
             unpack8(dr[u], t0);
 #pragma unroll
@@ -382,20 +382,14 @@ __global__ void __launch_bounds__(kEThreads, 3) blk_bwd_apply_kernel(const BlkBw
           }
         }
         unpack8(ar[u], av);
-        lds8(sP + 2 * C + c0, t0);
-        lds8(sP + 3 * C + c0, t1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = d[j] * t0[j] - t1[j];      // g - S1/n
         lds8(sP + c0, t0);
         lds8(sP + C + c0, t1);
-        float xh[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xh[j] = (av[j] - t0[j]) * t1[j];
-        lds8(sP + 4 * C + c0, t0);
-        lds8(sP + 5 * C + c0, t1);
+        for (int j = 0; j < 8; ++j) d[j] = d[j] * t0[j] + av[j] * t1[j];
+        lds8(sP + 2 * C + c0, t0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float z = t1[j] * (d[j] - xh[j] * t0[j]);
+          float z = d[j] + t0[j];
           if (av[j] <= 0.f) z *= a.slope_a;
           d[j] = z;
         }
@@ -668,7 +662,7 @@ int lun_block_bwd_apply_bf16(const void* dpre, const float* gpool, const void* o
   a.inv_n = 1.f / ((float)B * (float)HW);
   const int lanes = kEThreads / (C / 8);
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
-  blk_bwd_apply_kernel<<<grid, kEThreads, (7 * C + (dbias ? lanes * C : 0)) * sizeof(float), (cudaStream_t)stream>>>(a);
+  blk_bwd_apply_kernel<<<grid, kEThreads, (4 * C + (dbias ? lanes * C : 0)) * sizeof(float), (cudaStream_t)stream>>>(a);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }

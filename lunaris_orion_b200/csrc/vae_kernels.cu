@@ -9,11 +9,23 @@ namespace lun {
 
 constexpr int kVT = 256;
 
-__device__ __forceinline__ float softplus_f(float v) { return v > 20.f ? v : log1pf(__expf(v)); }
-__device__ __forceinline__ float mish_f(float v) { return v * tanhf(softplus_f(v)); }
+// mish(v) = v * tanh(softplus(v)). With e = exp(v): tanh(log(1+e)) = n / (n + 2), n = e^2 + 2e  (one exp, one divide;
+// for v > 20 tanh(softplus) == 1 in fp32, which is also torch's softplus threshold).
+__device__ __forceinline__ float mish_tanh_sp(float v, float* e_out) {
+  const float e = __expf(fminf(v, 20.f));
+  *e_out = e;
+  const float n = e * (e + 2.f);
+  return v > 20.f ? 1.f : __fdividef(n, n + 2.f);
+}
+__device__ __forceinline__ float mish_f(float v) {
+  float e;
+  return v * mish_tanh_sp(v, &e);
+}
+// d mish / dv = t + v * (1 - t^2) * sigmoid(v),  t = tanh(softplus(v)),  sigmoid(v) = e / (1 + e)
 __device__ __forceinline__ float mish_grad_f(float v) {
-  const float t = tanhf(softplus_f(v));
-  const float sg = 1.f / (1.f + __expf(-v));
+  float e;
+  const float t = mish_tanh_sp(v, &e);
+  const float sg = v > 20.f ? 1.f : __fdividef(e, 1.f + e);
   return t + v * (1.f - t * t) * sg;
 }
 
