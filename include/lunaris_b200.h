@@ -199,6 +199,17 @@ int lun_sprites_u8_to_f32(const void* u8_nhwc, float* out_nchw, int B, int H, in
 int lun_flash_attn2d_bf16(const void* qk, const void* v, const void* x, void* y, const float* gamma, int B, int N,
                           int C, void* stream);
 
+/* Optimizer boundary (train_hybrid.py:906-922): clip_grad_norm_(max_norm) + AdamW over all tensors of one model in two
+ * multi-tensor launches. table: device array of {float* param, grad, exp_avg, exp_avg_sq; long long numel} (40 bytes
+ * each); chunks: device array of int2 {tensor index, chunk index} with 8192 elements per chunk; norm2: device float,
+ * zeroed by the caller, receives sum g^2 and is read by the update (no host sync). bias_c1 = 1 - beta1^t,
+ * bias_c2_sqrt = sqrt(1 - beta2^t). Semantics = torch.optim.AdamW (decoupled decay, eps outside the bias-corrected
+ * sqrt) on the gradients scaled in place by min(1, max_norm / (norm + 1e-6)). */
+int lun_multi_grad_sumsq(const void* table, const void* chunks, int nchunks, float* norm2, void* stream);
+int lun_multi_clip_adamw(const void* table, const void* chunks, int nchunks, const float* norm2, float max_norm,
+                         float lr, float beta1, float beta2, float eps, float weight_decay, float bias_c1,
+                         float bias_c2_sqrt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -480,9 +480,7 @@ class _VaeLossFn(torch.autograd.Function):
         check(lib.lun_vae_loss_fwd(recon.data_ptr(), images.data_ptr(), mulv.data_ptr(), sums.data_ptr(),
                                    recon.numel(), B, L, _stream()), "lun_vae_loss_fwd")
         ctx.save_for_backward(recon, images, mulv)
-        scale = torch.tensor([1.0 / recon.numel(), -0.5 / (B * L)], device=recon.device)
-        out = sums * scale
-        return out[0], out[1]
+        return sums[0] * (1.0 / recon.numel()), sums[1] * (-0.5 / (B * L))     # python scalars: no H2D copy
 
     @staticmethod
     def backward(ctx, g_recon, g_kl):

@@ -21,6 +21,7 @@ from torch.optim.lr_scheduler import CosineAnnealingWarmRestarts
 
 from .lunar_evaluator import LunarMoETeacher
 from .lunar_generate import LunarisCoreVAE, sprites_to_tensor, vae_losses
+from .optim import ClipAdamW
 
 METRIC_KEYS = ("recon_loss", "kl_loss", "quality_loss", "pg_loss", "semantic_reward", "quality_reward", "baseline",
                "advantage", "vae_loss", "teacher_loss", "total_loss", "quality_scores")
@@ -200,9 +201,10 @@ class TrainingManager:
         # per-rank dropout / epsilon streams
         torch.manual_seed(args.seed + self.rank)
         torch.cuda.manual_seed_all(args.seed + self.rank)
-        mk = dict(weight_decay=args.weight_decay, betas=(0.9, 0.999), fused=True)
-        self.vae_optimizer = torch.optim.AdamW(self.vae.parameters(), lr=args.vae_lr, **mk)
-        self.teacher_optimizer = torch.optim.AdamW(self.teacher.parameters(), lr=args.teacher_lr, **mk)
+        # clip_grad_norm_ + AdamW fused into two multi-tensor launches per model (state layout == torch.optim.AdamW)
+        mk = dict(weight_decay=args.weight_decay, betas=(0.9, 0.999), max_grad_norm=args.max_grad_norm)
+        self.vae_optimizer = ClipAdamW(self.vae.parameters(), lr=args.vae_lr, **mk)
+        self.teacher_optimizer = ClipAdamW(self.teacher.parameters(), lr=args.teacher_lr, **mk)
         sk = dict(T_0=args.scheduler_t0, T_mult=2, eta_min=args.min_lr)
         self.vae_scheduler = CosineAnnealingWarmRestarts(self.vae_optimizer, **sk)
         self.teacher_scheduler = CosineAnnealingWarmRestarts(self.teacher_optimizer, **sk)
@@ -255,9 +257,7 @@ class TrainingManager:
         if boundary:
             if self.reducer is not None:
                 self.reducer.finish()
-            torch.nn.utils.clip_grad_norm_(self.vae.parameters(), a.max_grad_norm, foreach=True)
-            torch.nn.utils.clip_grad_norm_(self.teacher.parameters(), a.max_grad_norm, foreach=True)
-            self.vae_optimizer.step()
+            self.vae_optimizer.step()                    # clip (train_hybrid.py:913-915) happens inside the fused step
             self.teacher_optimizer.step()
             self.vae_scheduler.step()
             self.teacher_scheduler.step()

@@ -103,3 +103,36 @@ def test_training_makes_progress_and_stays_finite(cuda_dev, tmp_path):
     assert torch.equal(frozen0, tm.teacher.experts[0][1].conv1[0].weight.detach())
     assert not torch.equal(live0, tm.teacher.experts[0][1].conv2[0].weight.detach())
     assert tm.global_step == 10
+
+
+@pytest.mark.gpu
+def test_clip_adamw_matches_torch_clip_plus_adamw(cuda_dev):
+    """lunaris_orion_b200.optim.ClipAdamW == clip_grad_norm_(max_norm) + torch.optim.AdamW over several steps, with a
+    parameter that never receives a gradient (reference None-set) and an identical state_dict layout."""
+    from lunaris_orion_b200.optim import ClipAdamW
+    g = torch.Generator().manual_seed(0)
+    shapes = [(64, 32, 3, 3), (512,), (1, 48, 1, 1), (300, 7)]
+    pa = [torch.randn(s, generator=g).to(cuda_dev).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    dead_a = torch.zeros(5, device=cuda_dev, requires_grad=True)
+    dead_b = torch.zeros(5, device=cuda_dev, requires_grad=True)
+    oa = ClipAdamW(pa + [dead_a], lr=3e-3, weight_decay=0.01, max_grad_norm=1.0)
+    ob = torch.optim.AdamW(pb + [dead_b], lr=3e-3, weight_decay=0.01, betas=(0.9, 0.999))
+    for step in range(4):
+        for p, q in zip(pa, pb):
+            gr = torch.randn(p.shape, generator=g).to(cuda_dev) * (10.0 if step % 2 == 0 else 0.01)
+            p.grad, q.grad = gr.clone(), gr.clone()
+        torch.nn.utils.clip_grad_norm_(pb + [dead_b], 1.0)
+        ob.step()
+        oa.step()
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), step
+            assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-8), step
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert sa["state"][k].keys() == sb["state"][k].keys()
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 4.0
+        assert torch.allclose(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+    assert set(sb["param_groups"][0].keys()) <= set(sa["param_groups"][0].keys())
+    assert dead_a.grad is None and len(oa.state[dead_a]) == 0

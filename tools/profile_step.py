@@ -35,3 +35,16 @@ for e in prof.events():
         b[key][1] += e.device_time
 for k, v in sorted(b.items(), key=lambda kv: -kv[1][1])[:12]:
     print(k, v[0], f"{v[1]/1e3:.2f} ms")
+
+# ---- idle gaps on the GPU timeline
+ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.device_time > 0],
+            key=lambda e: e.time_range.start)
+gaps = []
+for a, b_ in zip(ev[:-1], ev[1:]):
+    gap = b_.time_range.start - a.time_range.end
+    if gap > 30:
+        gaps.append((gap, a.name[:50], b_.name[:50]))
+span = ev[-1].time_range.end - ev[0].time_range.start
+print(f"timeline span {span/1e3:.1f} ms, sum of gaps > 30us: {sum(g[0] for g in gaps)/1e3:.1f} ms in {len(gaps)} gaps")
+for g in sorted(gaps, reverse=True)[:14]:
+    print(f"  {g[0]:8.0f} us  after {g[1]}  before {g[2]}")
