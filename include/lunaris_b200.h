@@ -201,8 +201,8 @@ int lun_flash_attn2d_bf16(const void* qk, const void* v, const void* x, void* y,
 
 /* Optimizer boundary (train_hybrid.py:906-922): clip_grad_norm_(max_norm) + AdamW over all tensors of one model in two
  * multi-tensor launches. table: device array of {float* param, grad, exp_avg, exp_avg_sq; long long numel} (40 bytes
- * each); chunks: device array of int2 {tensor index, chunk index} with 8192 elements per chunk; norm2: device float,
- * zeroed by the caller, receives sum g^2 and is read by the update (no host sync). bias_c1 = 1 - beta1^t,
+ * each); chunks: device array of int2 {tensor index, chunk index} with 8192 elements per chunk; norm2: device float[1024]
+ * of per-block partial sums of g^2, summed in a fixed order by the update kernel (no host sync, bitwise reproducible). bias_c1 = 1 - beta1^t,
  * bias_c2_sqrt = sqrt(1 - beta2^t). Semantics = torch.optim.AdamW (decoupled decay, eps outside the bias-corrected
  * sqrt) on the gradients scaled in place by min(1, max_norm / (norm + 1e-6)). */
 int lun_multi_grad_sumsq(const void* table, const void* chunks, int nchunks, float* norm2, void* stream);

@@ -38,15 +38,22 @@ __global__ void __launch_bounds__(256) multi_sumsq_kernel(const OptTensor* __res
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int i = 0; i < 8; ++i) tot += s[i];
-    atomicAdd(norm2, tot);
-  }
+    norm2[blockIdx.x] = tot;     // per-block partial: the final sum is taken in a fixed order (bitwise reproducible,
+  }                              // so data-parallel ranks that hold identical gradients take identical steps)
 }
 
 __global__ void __launch_bounds__(256) multi_adamw_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ chunks,
-                                                          int nchunks, const float* __restrict__ norm2, float max_norm,
-                                                          float lr, float beta1, float beta2, float eps, float wd,
-                                                          float bias_c1, float bias_c2_sqrt) {
-  const float norm = sqrtf(norm2[0]);
+                                                          int nchunks, const float* __restrict__ norm2, int npart,
+                                                          float max_norm, float lr, float beta1, float beta2,
+                                                          float eps, float wd, float bias_c1, float bias_c2_sqrt) {
+  __shared__ float s_norm2;
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < npart; ++i) tot += norm2[i];
+    s_norm2 = tot;
+  }
+  __syncthreads();
+  const float norm = sqrtf(s_norm2);
   const float coef = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
   const float step_size = lr / bias_c1;
   const float decay = 1.f - lr * wd;
@@ -75,7 +82,7 @@ extern "C" {
 
 int lun_multi_grad_sumsq(const void* table, const void* chunks, int nchunks, float* norm2, void* stream) {
   if (nchunks <= 0) return LUN_OK;
-  int grid = nchunks < 148 * 8 ? nchunks : 148 * 8;
+  int grid = nchunks < 1024 ? nchunks : 1024;      // == number of partial sums written to norm2[]
   multi_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const OptTensor*)table, (const int2*)chunks, nchunks,
                                                             norm2);
   lun::note_launch(1);
@@ -87,9 +94,10 @@ int lun_multi_clip_adamw(const void* table, const void* chunks, int nchunks, con
                          float bias_c2_sqrt, void* stream) {
   if (nchunks <= 0) return LUN_OK;
   int grid = nchunks < 148 * 8 ? nchunks : 148 * 8;
+  const int npart = nchunks < 1024 ? nchunks : 1024;
   multi_adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const OptTensor*)table, (const int2*)chunks, nchunks,
-                                                            norm2, max_norm, lr, beta1, beta2, eps, weight_decay,
-                                                            bias_c1, bias_c2_sqrt);
+                                                            norm2, npart, max_norm, lr, beta1, beta2, eps,
+                                                            weight_decay, bias_c1, bias_c2_sqrt);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }

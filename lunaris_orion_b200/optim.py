@@ -59,7 +59,7 @@ class ClipAdamW(torch.optim.AdamW):
         ch = np.array(chunks, dtype=np.int32)
         tab_d = torch.from_numpy(tab).pin_memory().to(dev, non_blocking=True)
         ch_d = torch.from_numpy(ch).pin_memory().to(dev, non_blocking=True)
-        norm2 = torch.zeros(1, device=dev, dtype=torch.float32)
+        norm2 = torch.empty(1024, device=dev, dtype=torch.float32)     # per-block partials of sum g^2
         check(lib.lun_multi_grad_sumsq(tab_d.data_ptr(), ch_d.data_ptr(), len(chunks), norm2.data_ptr(), stream),
               "lun_multi_grad_sumsq")
         b1, b2 = group["betas"]
