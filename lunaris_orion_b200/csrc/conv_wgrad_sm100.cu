@@ -22,7 +22,6 @@ int num_sms();
 bool tile_grid(int GB, int GH, int GW, int pixels, int* TB, int* TH, int* TW);
 
 constexpr int kWgThreads = 192;
-constexpr int kWgABytes = 128 * 128;  // 64 pixels x 128 channels bf16
 constexpr int kWgXBox = 66 * 128;     // reuse3: 66 pixel rows (one halo pixel each side) x 64 channels
 constexpr int kWgXSlot = 9 * 1024;    // ... in a 1024-byte aligned slot
 

@@ -79,6 +79,33 @@ __device__ __forceinline__ void group_stats(const float* __restrict__ st, int C,
   *rstd = rsqrtf(var + eps);
 }
 
+
+// Group statistics of image b computed ONCE per block into shared memory: sg[g] = {mean, rstd}; with red != null also
+// the gamma-weighted backward sums sg[groups + g] = {S1/m, S2/m}. Thread i < groups reduces group i.
+__device__ __forceinline__ void block_group_stats(const float* __restrict__ st, const float* __restrict__ red,
+                                                  const float* __restrict__ gamma, int C, int groups, float inv_m,
+                                                  float eps, float2* sg) {
+  const int cpg = C / groups;
+  if ((int)threadIdx.x < groups) {
+    const int g0 = threadIdx.x * cpg;
+    float s1 = 0.f, s2 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      s1 += st[g0 + k];
+      s2 += st[C + g0 + k];
+      if (red) {
+        t1 += gamma[g0 + k] * red[g0 + k];
+        t2 += gamma[g0 + k] * red[C + g0 + k];
+      }
+    }
+    const float m = s1 * inv_m;
+    float var = s2 * inv_m - m * m;
+    var = var < 0.f ? 0.f : var;
+    sg[threadIdx.x] = make_float2(m, rsqrtf(var + eps));
+    if (red) sg[groups + threadIdx.x] = make_float2(t1 * inv_m, t2 * inv_m);
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------- GroupNorm + Mish forward
 // y = mish(gn(x));  if (res) y = mish(y + res);  if (add) y = y + add      (lunar_generate.py:37-38,53,96-97,212-222)
 __global__ void __launch_bounds__(kVT) gn_mish_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
@@ -86,18 +113,19 @@ __global__ void __launch_bounds__(kVT) gn_mish_fwd_kernel(const bf16* __restrict
                                                           const float* __restrict__ beta, const bf16* __restrict__ res,
                                                           const bf16* __restrict__ add, bf16* __restrict__ y, int HW,
                                                           int C, int groups, float eps) {
+  __shared__ float2 sg[64];
   const int cg = C >> 3, lanes = kVT / cg;
   const int cgi = threadIdx.x % cg, lane_px = threadIdx.x / cg;
-  if (lane_px >= lanes) return;
   const int b = blockIdx.y, c0 = cgi * 8, cpg = C / groups;
   const float inv_m = 1.f / ((float)cpg * (float)HW);
+  block_group_stats(stats + (size_t)b * 2 * C, nullptr, nullptr, C, groups, inv_m, eps, sg);
+  if (lane_px >= lanes) return;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float mean, rstd;
-    group_stats(stats + (size_t)b * 2 * C, C, cpg, c0 + j, inv_m, eps, &mean, &rstd);
-    sc[j] = gamma[c0 + j] * rstd;
-    sh[j] = beta[c0 + j] - mean * sc[j];
+    const float2 ms = sg[(c0 + j) / cpg];
+    sc[j] = gamma[c0 + j] * ms.y;
+    sh[j] = beta[c0 + j] - ms.x * sc[j];
   }
   for (int p = blockIdx.x * lanes + lane_px; p < HW; p += gridDim.x * lanes) {
     const size_t off = ((size_t)b * HW + p) * C + c0;
@@ -140,23 +168,23 @@ __global__ void __launch_bounds__(kVT) gn_mish_bwd_kernel(const bf16* __restrict
   const bool active = lane_px < lanes;
   const int b = blockIdx.y, c0 = cgi * 8, cpg = C / groups;
   const float inv_m = 1.f / ((float)cpg * (float)HW);
+  __shared__ float2 sg[128];
+  block_group_stats(stats + (size_t)b * 2 * C, PASS == 1 ? red + (size_t)b * 2 * C : nullptr, gamma, C, groups, inv_m,
+                    eps, sg);
   float mean[8], rstd[8], gm[8], bt[8], s1[8], s2[8], a1[8] = {}, a2[8] = {};
   if (active) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = c0 + j;
-      group_stats(stats + (size_t)b * 2 * C, C, cpg, c, inv_m, eps, &mean[j], &rstd[j]);
+      const float2 ms = sg[c / cpg];
+      mean[j] = ms.x;
+      rstd[j] = ms.y;
       gm[j] = gamma[c];
       bt[j] = beta[c];
       if (PASS == 1) {
-        const int g0 = (c / cpg) * cpg;
-        float t1 = 0.f, t2 = 0.f;
-        for (int k = 0; k < cpg; ++k) {
-          t1 += gamma[g0 + k] * red[(size_t)b * 2 * C + g0 + k];
-          t2 += gamma[g0 + k] * red[(size_t)b * 2 * C + C + g0 + k];
-        }
-        s1[j] = t1 * inv_m;
-        s2[j] = t2 * inv_m;
+        const float2 ts = sg[groups + c / cpg];
+        s1[j] = ts.x;
+        s2[j] = ts.y;
       }
     }
     for (int p = blockIdx.x * lanes + lane_px; p < HW; p += gridDim.x * lanes) {
@@ -317,49 +345,86 @@ __global__ void __launch_bounds__(256) conv3x3_c3_wgrad_kernel(const bf16* __res
 
 // ------------------------------------------------------------------------------------------- final conv 32->3 + tanh
 // recon[b,o,h,w] = tanh(conv3x3(x_nhwc[b], w[o]) + bias[o]), NCHW fp32 output (lunar_generate.py:226-228).
+// N = 3 outputs is far too thin for tcgen05 tiles, so each warp runs warp-level mma.sync m16n8k16 (bf16, fp32 acc):
+// M = 16 consecutive pixels of one image row (2 M-tiles per warp), N = 8 (3 used), K = 9 taps x 32 channels.
+// A fragments are 4-byte loads straight from the NHWC tensor (tap shift = pixel offset, zero outside the image),
+// B fragments (weights) are built once per warp.
 __global__ void __launch_bounds__(256) final_conv_tanh_fwd_kernel(const bf16* __restrict__ x,
                                                                   const float* __restrict__ w,
                                                                   const float* __restrict__ bias,
                                                                   float* __restrict__ recon, int B, int H, int W) {
-  __shared__ float sw[9][3][32];
-  for (int i = threadIdx.x; i < 864; i += 256) {
-    const int o = i / 288, ci = (i / 9) % 32, t = i % 9;    // reference layout [o][ci][kh][kw]
-    sw[t][o][ci] = rbf(w[i]);
-  }
-  __syncthreads();
-  const long total = (long)B * H * W;
-  const long p = (long)blockIdx.x * 256 + threadIdx.x;
-  if (p >= total) return;
-  const int b = (int)(p / ((long)H * W)), r = (int)(p % ((long)H * W)), h = r / W, wq = r % W;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  // B fragment of (tap, k-half): b0 = W[k = 2t, 2t+1][n = g], b1 = W[k = 2t+8, 2t+9][n = g]; n >= 3 is zero padding
+  uint32_t bfrag[9][2][2];
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int ih = h + kh - 1;
-    if (ih < 0 || ih >= H) continue;
+  for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int iw = wq + kw - 1;
-      if (iw < 0 || iw >= W) continue;
-      const bf16* xp = x + (((long)b * H + ih) * W + iw) * 32;
-      const int t = kh * 3 + kw;
+    for (int kh = 0; kh < 2; ++kh)
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float v[8];
-        load8(xp + c8 * 8, v);
+      for (int r = 0; r < 2; ++r) {
+        float w0 = 0.f, w1 = 0.f;
+        if (g < 3) {
+          const int ci = kh * 16 + r * 8 + 2 * t;
+          w0 = w[(g * 32 + ci) * 9 + tap];          // reference layout [o][ci][kh][kw]
+          w1 = w[(g * 32 + ci + 1) * 9 + tap];
+        }
+        __nv_bfloat162 p = __floats2bfloat162_rn(w0, w1);
+        bfrag[tap][kh][r] = *reinterpret_cast<uint32_t*>(&p);
+      }
+  const float b_lo = (2 * t < 3) ? bias[2 * t] : 0.f, b_hi = (2 * t + 1 < 3) ? bias[2 * t + 1] : 0.f;
+  const long hw = (long)H * W;
+  const long ngroups = (long)B * H * (W / 32);      // one warp per 32 consecutive pixels of a row
+  const long warp0 = ((long)blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * 256) >> 5;
+  for (long grp = warp0; grp < ngroups; grp += nwarps) {
+    const int wseg = (int)(grp % (W / 32));
+    const int h = (int)((grp / (W / 32)) % H);
+    const int b = (int)(grp / ((long)(W / 32) * H));
+    float d[2][4] = {};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          a0 += v[j] * sw[t][0][c8 * 8 + j];
-          a1 += v[j] * sw[t][1][c8 * 8 + j];
-          a2 += v[j] * sw[t][2][c8 * 8 + j];
+    for (int kh3 = 0; kh3 < 3; ++kh3) {
+      const int ih = h + kh3 - 1;
+      if (ih < 0 || ih >= H) continue;
+      const bf16* rowp = x + ((long)b * H + ih) * W * 32;
+#pragma unroll
+      for (int kw3 = 0; kw3 < 3; ++kw3) {
+        const int tap = kh3 * 3 + kw3;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int w_lo = wseg * 32 + mt * 16 + g + kw3 - 1, w_hi = w_lo + 8;   // pixels of fragment rows g, g+8
+          const bool ok_lo = w_lo >= 0 && w_lo < W, ok_hi = w_hi >= 0 && w_hi < W;
+          const uint32_t* plo = reinterpret_cast<const uint32_t*>(rowp + (long)w_lo * 32);
+          const uint32_t* phi = reinterpret_cast<const uint32_t*>(rowp + (long)w_hi * 32);
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            uint32_t a[4];
+            a[0] = ok_lo ? __ldg(plo + kh * 8 + t) : 0u;          // row g,   k = 2t, 2t+1   (+16*kh)
+            a[1] = ok_hi ? __ldg(phi + kh * 8 + t) : 0u;          // row g+8
+            a[2] = ok_lo ? __ldg(plo + kh * 8 + 4 + t) : 0u;      // row g,   k = 2t+8, 2t+9
+            a[3] = ok_hi ? __ldg(phi + kh * 8 + 4 + t) : 0u;
+            asm volatile(
+                "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                "{%0, %1, %2, %3};"
+                : "+f"(d[mt][0]), "+f"(d[mt][1]), "+f"(d[mt][2]), "+f"(d[mt][3])
+                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[tap][kh][0]), "r"(bfrag[tap][kh][1]));
+          }
         }
       }
     }
+    // C fragment: d[.][0], d[.][1] = (pixel g, outputs 2t, 2t+1); d[.][2], d[.][3] = (pixel g+8, same outputs)
+    float* obase = recon + (long)b * 3 * hw + (long)h * W + wseg * 32;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int px = mt * 16 + g;
+      if (2 * t < 3) {
+        obase[(2 * t) * hw + px] = tanhf(rbf(d[mt][0] + b_lo));
+        obase[(2 * t) * hw + px + 8] = tanhf(rbf(d[mt][2] + b_lo));
+      }
+      if (2 * t + 1 < 3) {
+        obase[(2 * t + 1) * hw + px] = tanhf(rbf(d[mt][1] + b_hi));
+        obase[(2 * t + 1) * hw + px + 8] = tanhf(rbf(d[mt][3] + b_hi));
+      }
+    }
   }
-  const long hw = (long)H * W;
-  float* dst = recon + (long)b * 3 * hw + r;
-  dst[0] = tanhf(rbf(a0 + bias[0]));
-  dst[hw] = tanhf(rbf(a1 + bias[1]));
-  dst[2 * hw] = tanhf(rbf(a2 + bias[2]));
 }
 
 // dx[b,h,w,ci] = sum_{o,taps} dpre[b,o,h+1-kh,w+1-kw] * w[o][ci][kh][kw],  dpre = drecon * (1 - recon^2)
@@ -632,9 +697,11 @@ int lun_conv3x3_c3_wgrad(const void* dy, const float* x_nchw, float* dw, float* 
 
 int lun_final_conv_tanh_fwd(const void* x, const float* w, const float* bias, float* recon, int B, int H, int W,
                             void* stream) {
-  const long total = (long)B * H * W;
-  final_conv_tanh_fwd_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias,
-                                                                                          recon, B, H, W);
+  if (W % 32) return LUN_E_SHAPE;
+  const long groups = (long)B * H * (W / 32);
+  long blocks = (groups + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  final_conv_tanh_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, recon, B, H, W);
   lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }
