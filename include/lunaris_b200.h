@@ -195,9 +195,22 @@ int lun_sprites_u8_to_f32(const void* u8_nhwc, float* out_nchw, int B, int H, in
 /* SelfAttention2d (lunar_generate.py:56-78) as a flash-style tcgen05 kernel: y = gamma * softmax(q k^T) v + x over
  * all N = H*W positions of each image, no N x N matrix. qk: [B*N, 128] bf16 rows = [q | k], each zero-padded from
  * C/8 to 64 columns (the 1x1 query / key convs write it); v, x, y: [B, N, C] bf16; gamma: device scalar.
- * N % 128 == 0, C % 64 == 0, C/8 <= 64. */
+ * Optional (training): o_out [B, N, C] bf16 = softmax(q k^T) v and lse_out [B*N] fp32 = row logsumexp, kept for the
+ * backward; pass NULL for inference. N % 128 == 0, C % 64 == 0, C <= 512. */
 int lun_flash_attn2d_bf16(const void* qk, const void* v, const void* x, void* y, const float* gamma, int B, int N,
-                          int C, void* stream);
+                          int C, void* o_out, float* lse_out, void* stream);
+
+/* Backward of the same module (what autograd derives from lunar_generate.py:70-77), three steps:
+ *   prep: dsum[row] = sum_c dy[row,c] * o[row,c]; dgamma[0] += sum of all dsum (dgamma zeroed by the caller).
+ *   dv:   dv[B,N,C] bf16 = gamma * P^T dy              (P rebuilt from qk and lse)
+ *   dqk:  dqk[B*N,128] bf16 = gamma * [dS K | dS^T Q], dS = P o (dy v^T - dsum); two launches (queries, keys).
+ * dy: [B, N, C] bf16 gradient of y (the residual branch dx += dy is the caller's). */
+int lun_flash_attn2d_bwd_prep_bf16(const void* dy, const void* o, float* dsum, float* dgamma, long rows, int C,
+                                   void* stream);
+int lun_flash_attn2d_dv_bf16(const void* qk, const void* dy, const float* lse, const float* gamma, void* dv, int B,
+                             int N, int C, void* stream);
+int lun_flash_attn2d_dqk_bf16(const void* qk, const void* v, const void* dy, const float* lse, const float* dsum,
+                              const float* gamma, void* dqk, int B, int N, int C, void* stream);
 
 /* Optimizer boundary (train_hybrid.py:906-922): clip_grad_norm_(max_norm) + AdamW over all tensors of one model in two
  * multi-tensor launches. table: device array of {float* param, grad, exp_avg, exp_avg_sq; long long numel} (40 bytes

@@ -93,7 +93,12 @@ SIGNATURES = {
     "lun_vae_loss_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p],
     "lun_vae_loss_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p],
     "lun_sprites_u8_to_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
-    "lun_flash_attn2d_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "lun_flash_attn2d_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                              c_void_p, c_void_p],
+    "lun_flash_attn2d_bwd_prep_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p],
+    "lun_flash_attn2d_dv_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "lun_flash_attn2d_dqk_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int, c_void_p],
     "lun_multi_grad_sumsq": [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "lun_multi_clip_adamw": [c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
                              c_float, c_float, c_void_p],

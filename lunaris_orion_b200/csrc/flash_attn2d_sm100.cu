@@ -10,6 +10,11 @@
 // warps 2..5 = softmax + epilogue (each thread owns one query row: TMEM lane == row).
 // K tiles are [128 keys][64 (padded) dims] K-major; V tiles are [128 keys][64-channel atoms] N-major (MN-major B
 // operand straight from the NHWC tensor); P is the K-major A operand of the second GEMM.
+//
+// The same kernel computes the VALUE GRADIENT of the backward pass (lse_in != nullptr): the CTA owns 128 KEYS, streams
+// the query tiles, rebuilds P^T[key, query] = exp(k.q - lse[query]) in one pass (the row statistics were saved by the
+// forward) and accumulates dV = gamma * P^T dY with dY in the place of V. The query / key gradients are in
+// flash_attn2d_bwd_sm100.cu.
 #include "../../include/lunaris_b200.h"
 #include "conv_gemm.cuh"
 #include "launch_count.cuh"
@@ -39,7 +44,8 @@ struct __align__(16) FaBars {
 __global__ void __launch_bounds__(kFaThreads, 1)
 flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma, int N, int C,
-                    int vw) {
+                    int vw, const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ o_out,
+                    float* __restrict__ lse_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int vatoms = vw / 64;                       // 64-channel atoms of the value slice
@@ -53,6 +59,9 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
   const int qt = blockIdx.x, b = blockIdx.y, vs = blockIdx.z;
   const int ntiles = N / 128;
   const uint32_t tmem_cols = 512;
+  const bool dv_mode = lse_in != nullptr;           // backward: own tile = keys (qk columns 64..127), streamed = queries
+  const int first_pass = dv_mode ? 1 : 0;
+  const int own_col = dv_mode ? 64 : 0, other_col = dv_mode ? 0 : 64;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQK);
@@ -87,14 +96,14 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     if (lane == 0) {
       const long row0 = (long)b * N;
       mbar_expect_tx(&bars->q_full, kFaTileBytes);
-      tma_load_2d(sQ, &tmQK, &bars->q_full, 0, (int)(row0 + qt * 128));
+      tma_load_2d(sQ, &tmQK, &bars->q_full, own_col, (int)(row0 + qt * 128));
       int ks = 0, vsx = 0;
       uint32_t kph = 0, vph = 0;
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = first_pass; pass < 2; ++pass) {
         for (int j = 0; j < ntiles; ++j) {
           mbar_wait(&bars->k_empty[ks], kph ^ 1);
           mbar_expect_tx(&bars->k_full[ks], kFaTileBytes);
-          tma_load_2d(sK + ks * kFaTileBytes, &tmQK, &bars->k_full[ks], 64, (int)(row0 + j * 128));
+          tma_load_2d(sK + ks * kFaTileBytes, &tmQK, &bars->k_full[ks], other_col, (int)(row0 + j * 128));
           if (++ks == 2) { ks = 0; kph ^= 1; }
           if (pass == 1) {
             mbar_wait(&bars->v_empty[vsx], vph ^ 1);
@@ -114,7 +123,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     mbar_wait(&bars->q_full, 0);
     int ks = 0, vsx = 0;
     uint32_t kph = 0, vph = 0, sph = 0, pph = 0;
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = first_pass; pass < 2; ++pass) {
       for (int j = 0; j < ntiles; ++j) {
         mbar_wait(&bars->k_full[ks], kph);
         mbar_wait(&bars->s_empty, sph ^ 1);          // softmax warps finished reading the previous S
@@ -160,8 +169,8 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float m = -3.0e38f, l = 0.f;
     uint32_t sph = 0, peph = 0;
-    // pass A: row max and row sum
-    for (int j = 0; j < ntiles; ++j) {
+    // pass A: row max and row sum (the backward reads the saved statistics instead)
+    for (int j = 0; j < (dv_mode ? 0 : ntiles); ++j) {
       mbar_wait(&bars->s_full, sph);
       sph ^= 1;
       tc_fence_after();
@@ -186,7 +195,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       l = l * __expf(m - mn) + s;
       m = mn;
     }
-    const float inv_l = 1.f / l;
+    const float inv_l = dv_mode ? 1.f : 1.f / l;
     // pass B: P tiles
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(&bars->s_full, sph);
@@ -202,15 +211,25 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       mbar_wait(&bars->p_empty, peph ^ 1);           // previous P consumed by the PV MMAs
       peph ^= 1;
       // row `row` of P: 128 keys -> two 64-key atoms, 8 chunks of 16 bytes each, chunk index swizzled by row & 7
+      const float4* lse_t = reinterpret_cast<const float4*>(lse_in + (size_t)b * N + j * 128);   // dv_mode only
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t pk[4];
+          float sub[8];
+          if (dv_mode) {
+            const float4 l0 = __ldg(lse_t + c * 8 + g * 2), l1 = __ldg(lse_t + c * 8 + g * 2 + 1);
+            sub[0] = l0.x; sub[1] = l0.y; sub[2] = l0.z; sub[3] = l0.w;
+            sub[4] = l1.x; sub[5] = l1.y; sub[6] = l1.z; sub[7] = l1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sub[e] = m;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float p0 = __expf(__uint_as_float(r[c][g * 8 + 2 * e]) - m) * inv_l;
-            const float p1 = __expf(__uint_as_float(r[c][g * 8 + 2 * e + 1]) - m) * inv_l;
+            const float p0 = __expf(__uint_as_float(r[c][g * 8 + 2 * e]) - sub[2 * e]) * inv_l;
+            const float p1 = __expf(__uint_as_float(r[c][g * 8 + 2 * e + 1]) - sub[2 * e + 1]) * inv_l;
             pk[e] = pack_bf16x2(p0, p1);
           }
           const int key0 = c * 32 + g * 8;             // first key of this 16-byte chunk
@@ -225,11 +244,12 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full);
     }
-    // epilogue: y = gamma * O + x
+    // epilogue: y = gamma * O + x  (backward: dV = gamma * O); training forward also keeps O and logsumexp
     mbar_wait(&bars->o_full, 0);
     tc_fence_after();
     const float gm = gamma[0];
     const size_t base = ((size_t)b * N + qt * 128 + row) * C + vs * vw;
+    if (lse_out != nullptr && vs == 0) lse_out[(size_t)b * N + qt * 128 + row] = m + __logf(l);
     for (int c0 = 0; c0 < vw; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_o + lane_addr + c0, r);
@@ -238,7 +258,8 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       uint4* ys = reinterpret_cast<uint4*>(y + base + c0);
 #pragma unroll
       for (int v4 = 0; v4 < 4; ++v4) {
-        const uint4 xv = __ldg(xs + v4);
+        uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+        if (!dv_mode) xv = __ldg(xs + v4);
         const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
         uint32_t o[4];
 #pragma unroll
@@ -247,6 +268,12 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
           o[e] = pack_bf16x2(gm * __uint_as_float(r[v4 * 8 + 2 * e]) + x0, gm * __uint_as_float(r[v4 * 8 + 2 * e + 1]) + x1);
         }
         ys[v4] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (o_out != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = pack_bf16x2(__uint_as_float(r[v4 * 8 + 2 * e]), __uint_as_float(r[v4 * 8 + 2 * e + 1]));
+          reinterpret_cast<uint4*>(o_out + base + c0)[v4] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
     }
   }
@@ -262,11 +289,9 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
 
 using namespace lun;
 
-extern "C" {
-
-int lun_flash_attn2d_bf16(const void* qk, const void* v, const void* x, void* y, const float* gamma, int B, int N,
-                          int C, void* stream) {
-  if (N % 128 || C % 64) return LUN_E_SHAPE;
+static int launch_flash(const void* qk, const void* v, const void* x, void* y, const float* gamma, int B, int N, int C,
+                        const float* lse_in, void* o_out, float* lse_out, void* stream) {
+  if (N % 128 || C % 64 || C > 512) return LUN_E_SHAPE;
   const int vw = C > 256 ? 256 : C;
   if (C % vw) return LUN_E_SHAPE;
   CUtensorMap tmQK, tmV;
@@ -284,10 +309,23 @@ int lun_flash_attn2d_bf16(const void* qk, const void* v, const void* x, void* y,
     configured = true;
   }
   dim3 grid(N / 128, B, C / vw);
-  flash_attn2d_kernel<<<grid, kFaThreads, smem, (cudaStream_t)stream>>>(tmQK, tmV, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, N,
-                                                                        C, vw);
+  flash_attn2d_kernel<<<grid, kFaThreads, smem, (cudaStream_t)stream>>>(
+      tmQK, tmV, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, N, C, vw, lse_in, (__nv_bfloat16*)o_out, lse_out);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+extern "C" {
+
+int lun_flash_attn2d_bf16(const void* qk, const void* v, const void* x, void* y, const float* gamma, int B, int N,
+                          int C, void* o_out, float* lse_out, void* stream) {
+  return launch_flash(qk, v, x, y, gamma, B, N, C, nullptr, o_out, lse_out, stream);
+}
+
+int lun_flash_attn2d_dv_bf16(const void* qk, const void* dy, const float* lse, const float* gamma, void* dv, int B,
+                             int N, int C, void* stream) {
+  if (lse == nullptr) return LUN_E_SHAPE;
+  return launch_flash(qk, dy, nullptr, dv, gamma, B, N, C, lse, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -47,41 +47,87 @@ class SelfAttention2d(nn.Module):
         self.gamma = nn.Parameter(torch.zeros(1))
 
     def forward(self, x):
-        """y = gamma * softmax(q^T k) v + x (lunar_generate.py:66-78) through the flash-style tcgen05 kernel
-        (csrc/flash_attn2d_sm100.cu). Forward only: the reference never instantiates this class, and its backward
-        kernel is not built - a call that needs gradients raises instead of silently detaching."""
+        """y = gamma * softmax(q^T k) v + x (lunar_generate.py:66-78) through the flash-style tcgen05 kernels
+        (csrc/flash_attn2d_sm100.cu forward + value gradient, csrc/flash_attn2d_bwd_sm100.cu query / key gradients).
+        The N x N attention matrix is never formed in either direction."""
         if not x.is_cuda:
             raise _capi.LunarisB200Error("lunaris_orion_b200 runs on CUDA (sm_100a) only; there is no CPU path")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise _capi.LunarisB200Error("SelfAttention2d backward is not implemented (forward / inference only)")
         B, C, H, W = x.shape
         N, dq = H * W, C // 8
         if N % 128 or C % 64 or dq > 64:
             raise _capi.LunarisB200Error("SelfAttention2d kernel needs H*W % 128 == 0, C % 64 == 0, C <= 512")
+        return _SelfAttention2dFn.apply(self, x, self.query_conv.weight, self.query_conv.bias, self.key_conv.weight,
+                                        self.key_conv.bias, self.value_conv.weight, self.value_conv.bias, self.gamma)
+
+
+class _SelfAttention2dFn(torch.autograd.Function):
+    """SelfAttention2d forward / backward on the flash kernels. Gradients: x, the three 1x1 convs, gamma."""
+
+    @staticmethod
+    def forward(ctx, mod, x, wq, bq, wk, bk, wv_p, bv, gamma):
+        B, C, H, W = x.shape
+        N, dq = H * W, C // 8
+        dev = x.device
         xf = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).view(B * N, C)
 
         def build_qk():
-            w = torch.zeros(128, C, device=x.device)
-            w[:dq] = self.query_conv.weight.detach().view(dq, C)
-            w[64:64 + dq] = self.key_conv.weight.detach().view(dq, C)
+            w = torch.zeros(128, C, device=dev)
+            w[:dq] = wq.detach().view(dq, C)
+            w[64:64 + dq] = wk.detach().view(dq, C)
             return w.to(torch.bfloat16).contiguous()
 
         def build_qk_bias():
-            bq = torch.zeros(128, device=x.device)
-            bq[:dq] = self.query_conv.bias.detach()
-            bq[64:64 + dq] = self.key_conv.bias.detach()
-            return bq.contiguous()
-        wqk = _cached((self.query_conv.weight, self.key_conv.weight), "sa_qk", build_qk)
-        bqk = _cached((self.query_conv.bias, self.key_conv.bias), "sa_qk_bias", build_qk_bias)
-        wv = _cached((self.value_conv.weight,), "sa_v", lambda: self.value_conv.weight.detach().view(C, C)
-                     .to(torch.bfloat16).contiguous())
+            b2 = torch.zeros(128, device=dev)
+            b2[:dq] = bq.detach()
+            b2[64:64 + dq] = bk.detach()
+            return b2.contiguous()
+        wqk = _cached((wq, wk), "sa_qk", build_qk)
+        bqk = _cached((bq, bk), "sa_qk_bias", build_qk_bias)
+        wv = _cached((wv_p,), "sa_v", lambda: wv_p.detach().view(C, C).to(torch.bfloat16).contiguous())
         qk = ops.linear_fprop(xf, wqk, bqk, out_f32=False)                       # [B*N, 128] = [q | k], zero padded
-        v = ops.linear_fprop(xf, wv, _f32(self.value_conv.bias), out_f32=False)  # [B*N, C]
-        y = torch.empty(B, N, C, device=x.device, dtype=torch.bfloat16)
-        check(_capi.lib().lun_flash_attn2d_bf16(qk.data_ptr(), v.data_ptr(), xf.data_ptr(), y.data_ptr(),
-                                                _f32(self.gamma).data_ptr(), B, N, C, _stream()),
-              "lun_flash_attn2d_bf16")
+        v = ops.linear_fprop(xf, wv, _f32(bv), out_f32=False)                    # [B*N, C]
+        y = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+        need = any(ctx.needs_input_grad)
+        o = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16) if need else None
+        lse = torch.empty(B * N, device=dev, dtype=torch.float32) if need else None
+        gm = _f32(gamma)
+        check(_capi.lib().lun_flash_attn2d_bf16(qk.data_ptr(), v.data_ptr(), xf.data_ptr(), y.data_ptr(), gm.data_ptr(),
+                                                B, N, C, _p(o), _p(lse), _stream()), "lun_flash_attn2d_bf16")
+        if need:
+            ctx.saved = (xf, qk, v, o, lse, wqk, wv, gm.clone())
+            ctx.dims = (B, C, H, W)
         return y.view(B, H, W, C).permute(0, 3, 1, 2).float()
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _capi.lib()
+        xf, qk, v, o, lse, wqk, wv, gm = ctx.saved
+        ctx.saved = None
+        B, C, H, W = ctx.dims
+        N, dq = H * W, C // 8
+        dev = dy.device
+        dyf = dy.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).view(B * N, C)
+        dsum = torch.empty(B * N, device=dev, dtype=torch.float32)
+        dgamma = torch.zeros(1, device=dev, dtype=torch.float32)
+        check(lib.lun_flash_attn2d_bwd_prep_bf16(dyf.data_ptr(), o.data_ptr(), dsum.data_ptr(), dgamma.data_ptr(),
+                                                 B * N, C, _stream()), "lun_flash_attn2d_bwd_prep_bf16")
+        dv = torch.empty(B * N, C, device=dev, dtype=torch.bfloat16)
+        check(lib.lun_flash_attn2d_dv_bf16(qk.data_ptr(), dyf.data_ptr(), lse.data_ptr(), gm.data_ptr(), dv.data_ptr(),
+                                           B, N, C, _stream()), "lun_flash_attn2d_dv_bf16")
+        dqk = torch.empty(B * N, 128, device=dev, dtype=torch.bfloat16)
+        check(lib.lun_flash_attn2d_dqk_bf16(qk.data_ptr(), v.data_ptr(), dyf.data_ptr(), lse.data_ptr(),
+                                            dsum.data_ptr(), gm.data_ptr(), dqk.data_ptr(), B, N, C, _stream()),
+              "lun_flash_attn2d_dqk_bf16")
+        # 1x1 convs: data gradients through the tcgen05 GEMM, weight gradients through the wgrad kernel
+        dx = dy.detach().permute(0, 2, 3, 1).reshape(B * N, C).float()
+        dx = dx + ops.linear_dgrad(dqk, wqk.t().contiguous()).float() + ops.linear_dgrad(dv, wv.t().contiguous()).float()
+        dwqk = ops.linear_wgrad(dqk, xf)                                          # [128, C]
+        dwv = ops.linear_wgrad(dv, xf)                                            # [C, C]
+        dbqk = dqk.float().sum(0)
+        grads = (None, dx.view(B, H, W, C).permute(0, 3, 1, 2),
+                 dwqk[:dq].reshape(dq, C, 1, 1), dbqk[:dq], dwqk[64:64 + dq].reshape(dq, C, 1, 1), dbqk[64:64 + dq],
+                 dwv.reshape(C, C, 1, 1), dv.float().sum(0), dgamma)
+        return tuple(g if need else None for g, need in zip(grads, ctx.needs_input_grad))
 
 
 class Encoder(nn.Module):
