@@ -28,6 +28,8 @@ extern "C" {
 #define LUN_EPI_LEAKY 2
 #define LUN_EPI_STATS 4
 #define LUN_EPI_OUT_F32 8
+#define LUN_EPI_STATS_IMG 64 /* with LUN_EPI_STATS: per-image sums, stats = fp32 [GB][2][Cout] (GroupNorm); the output
+                              * grid of one image must hold at least 128 pixels */
 
 /* Library / device probe: returns the SM count of the current device (148 on B200), <=0 on error. */
 int lun_num_sms(void);
@@ -170,6 +172,14 @@ int lun_conv3x3_c3_wgrad(const void* dy, const float* x_nchw, float* dw, float* 
  * backward: dx (NHWC bf16), dw [3,32,3,3], db [3] (caller zeroes dw, db). */
 int lun_final_conv_tanh_fwd(const void* x, const float* w, const float* bias, float* recon, int B, int H, int W,
                             void* stream);
+
+/* Decoder tail fused (lunar_generate.py:187-189 + 226-228): h = mish(groupnorm(t)) for the 32-channel up4 output,
+ * recon = tanh(conv3x3(h) + bias) in one pass over t. t: [B,H,W,32] bf16 raw ConvTranspose output; stats: [B,2,32]
+ * per-image channel sums (lun_image_channel_stats_bf16); h_out: optional [B,H,W,32] bf16 (kept for the backward, NULL
+ * when sampling); recon: [B,3,H,W] fp32. H % 16 == 0, W % 32 == 0. */
+int lun_gn_mish_final_conv_tanh_fwd(const void* t, const float* stats, const float* gamma, const float* beta,
+                                    const float* w, const float* bias, void* h_out, float* recon, int B, int H, int W,
+                                    int groups, float eps, void* stream);
 int lun_final_conv_bwd(const float* drecon, const float* recon, const void* x, const float* w, void* dx, float* dw,
                        float* db, int B, int H, int W, void* stream);
 

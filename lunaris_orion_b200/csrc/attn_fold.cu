@@ -7,8 +7,8 @@
 // so the kernel needs the attention INPUT rows x_j only: per (image, surviving row i) it computes, for all 8 heads,
 //     S[h][j] = qt[h] . x_j,   P = softmax_j(S) (+ attn_drop),   xbar[h] = sum_j P[h][j] x_j
 // where qt = (Wk_h^T Wq_h / sqrt(hd)) x_q + Wk_h^T bq_h / sqrt(hd) comes from one small GEMM and the head outputs
-// Wv_h xbar[h] + bv_h from another. Both contractions here are tiny (M = 8 heads): warp-level mma.sync m16n8k16 on
-// a shared-memory copy of the 32 x C chunk; the kernel is bound by reading the chunk once from HBM.
+// Wv_h xbar[h] + bv_h from another. Both contractions here are tiny (8 heads): warp-level mma.sync m16n8k16 on a
+// shared-memory copy of the 32 x C chunk; the kernel is bound by reading the chunk once from HBM.
 // The BatchNorm + Dropout2d affine of the attention input is applied while the chunk is staged, so the normalised
 // tensor x1 is never written to HBM either.
 #include "../../include/lunaris_b200.h"
@@ -19,18 +19,10 @@
 
 namespace lun {
 
-constexpr int kAfThreads = 128;
-
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -44,217 +36,252 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N_>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
-
-// Persistent blocks (4 warps) loop over items (image b, surviving row i); the raw 32 x C chunk of the NEXT item is
-// fetched with cp.async into the other half of a double buffer while the current one is contracted.
+// Persistent CTAs (8 warps, two per SM) each own a contiguous range of items (image b, surviving row i).
 // The BatchNorm + Dropout2d affine x = m*(s*y + t) never touches the 32 x C chunk:
 //     scores:  qt . x_j = (qt*m*s) . y_j + const            -> the queries are scaled once (8 x C values)
 //     output:  sum_j p_j x_j = m*(s * sum_j p_j y_j + t * sum_j p_j)   -> applied to the 8 x C result
 //   y     [B, N, C]        attention input BEFORE BatchNorm (conv1 output)
 //   qt    [B, nq_pad, 8*C] folded queries (head-major)
 //   xbar  [B, nq_pad, 8*C] output
-template <int C, int NBUF>
-__global__ void __launch_bounds__(kAfThreads) attn_fold_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
-                                                               const float* __restrict__ shift,
-                                                               const float* __restrict__ m2,
-                                                               const bf16* __restrict__ qt, bf16* __restrict__ xbar,
-                                                               int B, int N, int nq, int nq_pad,
-                                                               unsigned long long seed, unsigned int thresh16,
-                                                               float drop_scale) {
-  constexpr int PITCH = C + 8;                     // bf16 elements per smem row (+16 B: conflict-free ldmatrix)
+//   * the 32 x C chunk of the NEXT item travels by cp.async.bulk (one 2C-byte copy per token row, mbarrier
+//     completion) into the other half of a two-stage ring while the current item is contracted: no thread spends
+//     instructions or registers on the copy, and each of the two resident CTAs per SM always has a chunk in flight;
+//   * S^T = Y Q'^T  (M = tokens, N = 8 heads) and  out^T = Y^T P^T  (M = channels, N = 8 heads): with the 8 heads on
+//     the MMA's N side no half of an m16n8k16 tile is padding;
+//   * a CTA owns a contiguous range of items, so the per-image affine lives in registers and is reloaded only when
+//     the image changes; the 8 x C result leaves through shared memory and eight 2C-byte bulk stores.
+constexpr int kAfThreads = 256;
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kAfThreads, 2)
+attn_fold_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                  const float* __restrict__ m2, const bf16* __restrict__ qt, bf16* __restrict__ xbar, int B, int N,
+                  int nq, int nq_pad, unsigned long long seed, unsigned int thresh16, float drop_scale) {
+  constexpr int PITCH = C + 8;                      // bf16 per smem row: +16 B keeps ldmatrix conflict-free
   constexpr int CH8 = C / 8;
-  constexpr int NL = 32 * CH8 / kAfThreads;        // 16-byte chunk copies per thread
-  constexpr int NQ = (8 * CH8 + kAfThreads - 1) / kAfThreads;   // query chunks per thread
-  constexpr int RSTEP = kAfThreads / CH8;
-  static_assert(kAfThreads % CH8 == 0 && NL >= 1, "unsupported channel count");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* Xs0 = reinterpret_cast<bf16*>(smem_raw);            // [2][32][PITCH] raw chunk rows (tokens), double buffer
-  bf16* Qs = Xs0 + NBUF * 32 * PITCH;                       // [8][PITCH] scaled queries
-  float* Sp = reinterpret_cast<float*>(Qs + 8 * PITCH);     // [8 warps][8][32] partial scores
+  constexpr int NQ = (8 * CH8 + kAfThreads - 1) / kAfThreads;   // 16-byte query chunks per thread
+  constexpr int KQ = C / 4;                         // channels per K-quarter of the score contraction
+  constexpr int MT_TOTAL = C / 16;                  // 16-channel m-tiles of the output contraction
+  constexpr int MTW = MT_TOTAL >= 8 ? MT_TOTAL / 8 : 1;           // m-tiles per warp
+  constexpr int PV_WARPS = MT_TOTAL / MTW;
+  constexpr int SPS = 36;                           // padded token stride of the partial-score buffer (floats)
+  static_assert(kAfThreads % CH8 == 0 && KQ % 16 == 0, "unsupported channel count");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  bf16* Xs = reinterpret_cast<bf16*>(smem_raw);                  // [2][32][PITCH] chunk ring
+  bf16* Qs = Xs + 2 * 32 * PITCH;                                // [8][PITCH] scaled queries
+  bf16* Os = Qs + 8 * PITCH;                                     // [2][8][PITCH] results awaiting their bulk stores
+  float* Sp = reinterpret_cast<float*>(Os + 2 * 8 * PITCH);      // [4 K-quarters][8 heads][SPS]
+  uint32_t* Ps = reinterpret_cast<uint32_t*>(Sp + 4 * 8 * SPS);  // [8 heads][16] probabilities, bf16 pairs
+  float* Psum = reinterpret_cast<float*>(Ps + 8 * 16);           // [8]
+  uint64_t* full = reinterpret_cast<uint64_t*>(Psum + 8);        // [2]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
   const int nc = N / 32;
   const int items = B * nq;
-  const int c8 = tid % CH8, r0 = tid / CH8;
-  const int g = lane >> 2, t4 = lane & 3;
-  constexpr int NWARPS = kAfThreads / 32;
-  constexpr int NW = (C / 16 < NWARPS) ? C / 16 : NWARPS;   // warps that take part in the two contractions
-  constexpr int KW = C / NW;                       // channels per warp
+  const int per = (items + gridDim.x - 1) / gridDim.x;
+  const int it0 = blockIdx.x * per;
+  const int it1 = it0 + per < items ? it0 + per : items;
+  if (it0 >= it1) return;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
 
-  auto issue_chunk = [&](int item, int buf) {
-    const int b = item / nq, i = item % nq;
+  auto issue_chunk = [&](int b, int i, int stage) {   // one whole warp: one row copy per lane
     const int chunk = i < nc - 1 ? i : nc - 1;
-    const bf16* src = y + ((size_t)b * N + 32 * chunk + r0) * C + c8 * 8;
-    const uint32_t dst = smem_u32(Xs0 + (buf * 32 + r0) * PITCH + c8 * 8);
-#pragma unroll
-    for (int k = 0; k < NL; ++k) cp_async16(dst + k * RSTEP * PITCH * 2, src + (size_t)k * RSTEP * C);
-    cp_async_commit();
+    if (lane == 0) mbar_expect_tx(&full[stage], 32 * C * 2);
+    __syncwarp();
+    bulk_load(smem_u32(Xs + (stage * 32 + lane) * PITCH), y + ((size_t)b * N + 32 * chunk + lane) * C, C * 2,
+              &full[stage]);
   };
-
-  // query chunks owned by this thread: idx = tid + k*128 over [8 heads][CH8]; for C >= 128 the channel group of a
-  // thread is fixed (128 % CH8 == 0). Queries and the Dropout2d mask of the NEXT item are prefetched into registers
-  // while the current item is contracted.
-  auto load_q = [&](int item, uint4 (&q)[NQ], float4 (&mk)[NQ][2]) {
-    const int b = item / nq, i = item % nq;
+  auto load_q = [&](int b, int i, uint4 (&q)[NQ]) {
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
       const int idx = tid + k * kAfThreads;
-      if (idx < 8 * CH8) {
-        const int qc = (idx % CH8) * 8;
-        q[k] = __ldg(reinterpret_cast<const uint4*>(qt + (((size_t)b * nq_pad + i) * 8 + idx / CH8) * C + qc));
-        if (m2) {
-          mk[k][0] = __ldg(reinterpret_cast<const float4*>(m2 + (size_t)b * C + qc));
-          mk[k][1] = __ldg(reinterpret_cast<const float4*>(m2 + (size_t)b * C + qc + 4));
-        } else {
-          mk[k][0] = mk[k][1] = make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-      }
+      if (idx < 8 * CH8)
+        q[k] = __ldg(reinterpret_cast<const uint4*>(qt + (((size_t)b * nq_pad + i) * 8 + idx / CH8) * C + (idx % CH8) * 8));
     }
   };
-  int item = blockIdx.x;
+  // per-image affine in registers: ms = m*s for this thread's query channels; A = m*s, Bc = m*t for its output channels
+  const int qc = (tid % CH8) * 8;
+  float ms[8], pa[MTW][2], pb[MTW][2];
+  auto load_affine = [&](int b) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ms[j] = scale[qc + j] * (m2 ? m2[(size_t)b * C + qc + j] : 1.f);
+#pragma unroll
+    for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c = (warp * MTW + mt) * 16 + g + hh * 8;
+        const float mk = (m2 && c < C) ? m2[(size_t)b * C + c] : 1.f;
+        pa[mt][hh] = c < C ? mk * scale[c] : 0.f;
+        pb[mt][hh] = c < C ? mk * shift[c] : 0.f;
+      }
+  };
+  // (image, row) of an item, advanced incrementally (no division in the loop)
+  auto advance = [&](int& b, int& i) {
+    if (++i == nq) {
+      i = 0;
+      ++b;
+    }
+  };
+
+  int b = it0 / nq, i = it0 % nq;
   uint4 qraw[NQ];
-  float4 mraw[NQ][2];
-  if (item < items) {
-    issue_chunk(item, 0);
-    load_q(item, qraw, mraw);
+  {
+    int b1 = b, i1 = i;
+    advance(b1, i1);
+    if (warp == 0) issue_chunk(b, i, 0);
+    if (warp == 1 && it0 + 1 < it1) issue_chunk(b1, i1, 1);
   }
-  int buf = 0;
-  for (; item < items; item += gridDim.x, buf ^= (NBUF - 1)) {
-    const int b = item / nq, i = item % nq;
-    // stage this item's queries scaled by m*s, then prefetch the next item's
+  load_q(b, i, qraw);
+  int cur_b = -1;
+  const uint32_t qs_base = smem_u32(Qs);
+  const int mat = lane >> 3, lrow = lane & 7;
+
+  for (int item = it0; item < it1; ++item) {
+    const int n = item - it0, stage = n & 1;
+    int b1 = b, i1 = i;
+    advance(b1, i1);
+    if (b != cur_b) {
+      load_affine(b);
+      cur_b = b;
+    }
+    // ---- queries scaled by m*s -> Qs; next item's raw queries -> registers
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
       const int idx = tid + k * kAfThreads;
       if (idx < 8 * CH8) {
-        const int qc = (idx % CH8) * 8;
         float v[8];
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&qraw[k]);
+        unpack8(qraw[k], v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 t = __bfloat1622float2(h2[j]);
-          v[2 * j] = t.x;
-          v[2 * j + 1] = t.y;
-        }
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + qc));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + qc + 4));
-        v[0] *= s0.x * mraw[k][0].x; v[1] *= s0.y * mraw[k][0].y; v[2] *= s0.z * mraw[k][0].z; v[3] *= s0.w * mraw[k][0].w;
-        v[4] *= s1.x * mraw[k][1].x; v[5] *= s1.y * mraw[k][1].y; v[6] *= s1.z * mraw[k][1].z; v[7] *= s1.w * mraw[k][1].w;
+        for (int j = 0; j < 8; ++j) v[j] *= ms[j];
         store8(Qs + (idx / CH8) * PITCH + qc, v);
       }
     }
-    const int next = item + gridDim.x;
-    if (next < items) {
-      if (NBUF == 2) issue_chunk(next, buf ^ 1);
-      load_q(next, qraw, mraw);
-    }
-    if (NBUF == 2 && next < items) cp_async_wait<1>(); else cp_async_wait<0>();   // this item's chunk has landed
-    __syncthreads();
+    if (item + 1 < it1) load_q(b1, i1, qraw);
+    mbar_wait(&full[stage], (n >> 1) & 1);         // this item's chunk has landed
+    __syncthreads();                               // (1) Qs visible
 
-    // ---- S = Q' Y^T : each warp owns a quarter of the channel (k) range, partials are summed through smem
-    const uint32_t xs_base = smem_u32(Xs0 + buf * 32 * PITCH), qs_base = smem_u32(Qs);
-    float s[4][4];
+    // ---- S^T partial: warp -> (16-token m-tile, K-quarter)
+    const uint32_t xs_base = smem_u32(Xs + stage * 32 * PITCH);
+    {
+      const int mt = warp & 1, kq = warp >> 1;
+      float d[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};     // two accumulators: independent MMA chains
+      // A (tokens x k): matrices {tok 0-7,k 0-7}, {tok 8-15,k 0-7}, {tok 0-7,k 8-15}, {tok 8-15,k 8-15}
+      const uint32_t a_addr = xs_base + ((mt * 16 + lrow + (mat & 1) * 8) * PITCH + kq * KQ + (mat >> 1) * 8) * 2;
+      // B (heads x k) for two k-steps: {k 0-7}, {k 8-15}, {k 16-23}, {k 24-31}
+      const uint32_t b_addr = qs_base + (lrow * PITCH + kq * KQ + mat * 8) * 2;
 #pragma unroll
-    for (int n = 0; n < 4; ++n)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[n][e] = 0.f;
-#pragma unroll 2
-    for (int k0 = warp * KW; warp < NW && k0 < (warp + 1) * KW; k0 += 16) {
-      uint32_t a[4], a2[2];
-      ldsm_x2(a2, qs_base + ((lane & 7) * PITCH + k0 + ((lane >> 3) & 1) * 8) * 2);
-      a[0] = a2[0]; a[1] = 0u; a[2] = a2[1]; a[3] = 0u;          // rows 8..15 of the M=16 tile are padding
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        uint32_t bb[2];
-        ldsm_x2(bb, xs_base + ((n * 8 + (lane & 7)) * PITCH + k0 + ((lane >> 3) & 1) * 8) * 2);
-        mma_bf16_16816(s[n], a, bb);
+      for (int k0 = 0; k0 < KQ; k0 += 32) {
+        uint32_t bq[4], a0[4], a1[4];
+        ldsm_x4(bq, b_addr + k0 * 2);
+        ldsm_x4(a0, a_addr + k0 * 2);
+        if (k0 + 16 < KQ) ldsm_x4(a1, a_addr + (k0 + 16) * 2);
+        {
+          const uint32_t bb[2] = {bq[0], bq[1]};
+          mma_bf16_16816(d, a0, bb);
+        }
+        if (k0 + 16 < KQ) {
+          const uint32_t bb[2] = {bq[2], bq[3]};
+          mma_bf16_16816(e, a1, bb);
+        }
       }
+      // d0,d1: token g, heads 2t4, 2t4+1;  d2,d3: token g+8
+      float* sp = Sp + (kq * 8 + 2 * t4) * SPS + mt * 16 + g;
+      sp[0] = d[0] + e[0];
+      sp[SPS] = d[1] + e[1];
+      sp[8] = d[2] + e[2];
+      sp[SPS + 8] = d[3] + e[3];
     }
-    if (warp < NW) {
+    __syncthreads();                               // (2) partial scores visible
+
+    // ---- softmax: warp = head, lane = token (one probability per thread, reductions by shuffles)
+    {
+      float sc = Sp[warp * SPS + lane] + Sp[(8 + warp) * SPS + lane] + Sp[(16 + warp) * SPS + lane] +
+                 Sp[(24 + warp) * SPS + lane];
+      sc = rbf(sc);                                // the reference's scores are a bf16 tensor
+      float mx = sc;
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        float* sp = Sp + (warp * 8 + g) * 32 + n * 8 + t4 * 2;
-        sp[0] = s[n][0];
-        sp[1] = s[n][1];
-      }
-    }
-    __syncthreads();
-    // every warp rebuilds the full score fragment (rows = heads g, cols = tokens)
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      s[n][0] = 0.f;
-      s[n][1] = 0.f;
-    }
-#pragma unroll
-    for (int w = 0; w < NW; ++w)
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const float2 t = *reinterpret_cast<const float2*>(Sp + (w * 8 + g) * 32 + n * 8 + t4 * 2);
-        s[n][0] += t.x;
-        s[n][1] += t.y;
-      }
-    // ---- softmax over the 32 tokens of head g
-    float m0 = -3.0e38f;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      s[n][0] = rbf(s[n][0]);                      // the reference's scores are a bf16 tensor
-      s[n][1] = rbf(s[n][1]);
-      m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    float sum = 0.f;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      s[n][0] = __expf(s[n][0] - m0);
-      s[n][1] = __expf(s[n][1] - m0);
-      sum += s[n][0] + s[n][1];
-    }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    const float inv = 1.f / sum;
-    uint32_t pa[2][4];                             // P as A fragments of the two token k-steps
-    float psum = 0.f;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      float p0 = s[n][0] * inv, p1 = s[n][1] * inv;
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float ex = __expf(sc - mx);
+      float p = ex / warp_sum(ex);
       if (thresh16) {
-        const unsigned long long base = ((((unsigned long long)b * nq + i) * 8 + g) << 5) + n * 8 + t4 * 2;
-        p0 = drop_keep1(seed, base, thresh16) ? p0 * drop_scale : 0.f;
-        p1 = drop_keep1(seed, base + 1, thresh16) ? p1 * drop_scale : 0.f;
+        // same stream as drop_keep1(seed, ((b*nq + i)*8 + head) << 5 | token, .)
+        const unsigned long long base = (((unsigned long long)b * nq + i) * 8 + warp) << 5;
+        const uint32_t h = hash32(drop_key(seed, (base >> 3) + (lane >> 3)) + ((lane >> 1) & 3));
+        p = ((lane & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thresh16 ? p * drop_scale : 0.f;
       }
-      p0 = rbf(p0);
-      p1 = rbf(p1);
-      psum += p0 + p1;
-      pa[n >> 1][(n & 1) * 2] = pack2(p0, p1);     // rows g     (a0 / a2)
-      pa[n >> 1][(n & 1) * 2 + 1] = 0u;            // rows g + 8 (a1 / a3): padding heads contribute nothing
+      p = rbf(p);
+      const float psum = warp_sum(p);
+      const float pn = __shfl_down_sync(0xffffffffu, p, 1);
+      if (!(lane & 1)) Ps[warp * 16 + (lane >> 1)] = pack2(p, pn);
+      if (lane == 0) Psum[warp] = psum;
     }
-    psum += __shfl_xor_sync(0xffffffffu, psum, 1);
-    psum += __shfl_xor_sync(0xffffffffu, psum, 2);
-    // ---- Ybar = P Y, then xbar = m*(s*Ybar + t*psum); each warp owns a quarter of the output channels
-    bf16* out = xbar + (((size_t)b * nq_pad + i) * 8 + g) * C;
-#pragma unroll 4
-    for (int n0 = warp * KW; warp < NW && n0 < (warp + 1) * KW; n0 += 8) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
+    __syncthreads();                               // (3) probabilities visible
+
+    // ---- out^T = Y^T P^T: warp -> MTW m-tiles of 16 channels; xbar = A * d + Bc * psum
+    bf16* os = Os + stage * 8 * PITCH;
+    if (warp < PV_WARPS) {
+      // B fragments of P^T: [k-step][b0, b1] = head g, tokens 16ks + {2t4, 2t4+1}, {8+2t4, 9+2t4}
+      uint32_t pfrag[4];
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        uint32_t bb[2];
-        ldsm_x2_trans(bb, xs_base + ((kk * 16 + (lane & 15)) * PITCH + n0) * 2);
-        mma_bf16_16816(d, pa[kk], bb);
+      for (int nn = 0; nn < 4; ++nn) pfrag[nn] = Ps[g * 16 + nn * 4 + t4];
+      const float ps0 = Psum[2 * t4], ps1 = Psum[2 * t4 + 1];
+#pragma unroll
+      for (int mt = 0; mt < MTW; ++mt) {
+        const int c0 = (warp * MTW + mt) * 16;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          // A^T from [token][channel] storage: {tok 0-7,ch 0-7}, {tok 0-7,ch 8-15}, {tok 8-15,ch 0-7}, {tok 8-15,ch 8-15}
+          uint32_t a[4];
+          ldsm_x4_trans(a, xs_base + ((ks * 16 + lrow + (mat >> 1) * 8) * PITCH + c0 + (mat & 1) * 8) * 2);
+          const uint32_t bb[2] = {pfrag[2 * ks], pfrag[2 * ks + 1]};
+          mma_bf16_16816(d, a, bb);
+        }
+        // d0,d1: channel c0+g, heads 2t4, 2t4+1;  d2,d3: channel c0+g+8
+        os[(2 * t4) * PITCH + c0 + g] = __float2bfloat16_rn(pa[mt][0] * d[0] + pb[mt][0] * ps0);
+        os[(2 * t4 + 1) * PITCH + c0 + g] = __float2bfloat16_rn(pa[mt][0] * d[1] + pb[mt][0] * ps1);
+        os[(2 * t4) * PITCH + c0 + g + 8] = __float2bfloat16_rn(pa[mt][1] * d[2] + pb[mt][1] * ps0);
+        os[(2 * t4 + 1) * PITCH + c0 + g + 8] = __float2bfloat16_rn(pa[mt][1] * d[3] + pb[mt][1] * ps1);
       }
-      const int c = n0 + t4 * 2;
-      const float2 sc = *reinterpret_cast<const float2*>(scale + c), sh = *reinterpret_cast<const float2*>(shift + c);
-      float2 mk = make_float2(1.f, 1.f);
-      if (m2) mk = *reinterpret_cast<const float2*>(m2 + (size_t)b * C + c);
-      *reinterpret_cast<uint32_t*>(out + c) = pack2(mk.x * (sc.x * d[0] + sh.x * psum), mk.y * (sc.y * d[1] + sh.y * psum));
+      fence_proxy_async();                         // results visible to the bulk store
     }
-    __syncthreads();                               // Qs / Sp / this X buffer are rewritten by the next iterations
-    if (NBUF == 1 && next < items) issue_chunk(next, 0);
+    __syncthreads();                               // (4) chunk stage, Qs, Sp, Ps and Os[stage] are settled
+    if (warp == 0) {
+      if (lane < 8) {                              // one head row per lane
+        bulk_store(xbar + (((size_t)b * nq_pad + i) * 8 + lane) * C, smem_u32(os + lane * PITCH), C * 2);
+        // Os[stage ^ 1] is rewritten by the next item: its stores (committed one item ago) must have read it
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
+    } else if (warp == 1 && item + 2 < it1) {
+      int b2 = b1, i2 = i1;
+      advance(b2, i2);
+      issue_chunk(b2, i2, stage);
+    }
+    b = b1;
+    i = i1;
   }
+  if (tid < 8) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // out[b, i, :] = drop2d(bn(y[b, qtok(i), :])): the query rows of the as-executed attention with its input affine.
@@ -282,32 +309,19 @@ template <int C>
 static int launch_fold(const bf16* y, const float* scale, const float* shift, const float* m2, const bf16* qt,
                        bf16* xbar, int B, int N, int nq, int nq_pad, unsigned long long seed, unsigned int th,
                        float ds, cudaStream_t st) {
-  static int nbuf = 0;
-  if (!nbuf) {
-    const char* e = getenv("LUN_ATTN_NBUF");
-    nbuf = e ? atoi(e) : 1;
-    if (nbuf != 2) nbuf = 1;
-  }
-  const int smem = (32 * nbuf + 8) * (C + 8) * 2 + 8 * 8 * 32 * 4;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_fold_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_fold_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
-      return LUN_E_ATTR;
-    configured = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int per_sm = (224 * 1024) / (smem + 1024);
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  int grid = sms * per_sm;
-  if (grid > B * nq) grid = B * nq;
-  if (nbuf == 2)
-    attn_fold_kernel<C, 2><<<grid, kAfThreads, smem, st>>>(y, scale, shift, m2, qt, xbar, B, N, nq, nq_pad, seed, th, ds);
-  else
-    attn_fold_kernel<C, 1><<<grid, kAfThreads, smem, st>>>(y, scale, shift, m2, qt, xbar, B, N, nq, nq_pad, seed, th, ds);
+  const int smem = (2 * 32 + 8 + 2 * 8) * (C + 8) * 2 + 4 * 8 * 36 * 4 + 8 * 16 * 4 + 8 * 4 + 16;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_fold_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return LUN_E_ATTR;
+    configured = true;
+  }
+  long grid = 2L * sms;                              // two resident CTAs per SM, contiguous item ranges
+  if (grid > (long)B * nq) grid = (long)B * nq;
+  attn_fold_kernel<C><<<(int)grid, kAfThreads, smem, st>>>(y, scale, shift, m2, qt, xbar, B, N, nq, nq_pad, seed, th, ds);
   return LUN_OK;
 }
 

@@ -190,6 +190,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int half = ew >> 2;
     const int row = q * 32 + lane;      // accumulator row == pixel index inside the tile
     const bool do_stats = g.flags & EPI_STATS, out_f32 = g.flags & EPI_OUT_F32, tma_out = g.flags & EPI_TMA_STORE;
+    const bool stats_img = g.flags & EPI_STATS_IMG;
     const float slope = (g.flags & EPI_LEAKY) ? g.slope : 1.f;
     const bool half_leader = (threadIdx.x == 64 + half * 128);
     const uint32_t stg_base = smem_u32(s_stage) + half * 8192;
@@ -302,8 +303,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
             }
           }
-          atomicAdd(&s_stats[nb + lane], s1[0]);
-          atomicAdd(&s_stats[g.Cout + nb + lane], s2[0]);
+          if (stats_img) {
+            // GroupNorm: the tile lies inside image tb; one coalesced reduction per warp straight to global
+            float* st = stats + static_cast<size_t>(tb) * 2 * g.Cout + nb + lane;
+            atomicAdd(st, s1[0]);
+            atomicAdd(st + g.Cout, s2[0]);
+          } else {
+            atomicAdd(&s_stats[nb + lane], s1[0]);
+            atomicAdd(&s_stats[g.Cout + nb + lane], s2[0]);
+          }
         }
       };
       uint32_t ra[32], rb[32];
@@ -328,7 +336,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
     if (store_pending && half_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (do_stats) {
+    if (do_stats && !stats_img) {
       asm volatile("bar.sync 5, 256;" ::: "memory");
       for (int i = threadIdx.x - 64; i < 2 * g.Cout; i += 256) atomicAdd(stats + i, s_stats[i]);
     }
@@ -428,6 +436,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   g.ntb = (g.GB + g.TB - 1) / g.TB;
   if (g.TW * g.in_mul > 256 || g.TH * g.in_mul > 256 || g.TB > 256) return 5;
   if (g.Cout > 2048 && (g.flags & EPI_STATS)) return 6;
+  if ((g.flags & EPI_STATS_IMG) && (!(g.flags & EPI_STATS) || g.TB != 1)) return 6;
   if (!(g.flags & EPI_OUT_F32) && (g.ldo % 8 || g.o_coff % 8)) return 7;
 
   CUtensorMap tmA, tmA2, tmB, tmO;

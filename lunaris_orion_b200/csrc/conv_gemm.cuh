@@ -15,6 +15,8 @@ enum : int {
   EPI_STATS = 4,      // per-channel sum / sum-of-squares of the stored (rounded) values -> stats[0:N], stats[N:2N]
   EPI_OUT_F32 = 8,    // store fp32 instead of bf16
   EPI_TMA_STORE = 32, // (set by the launcher) bf16 output leaves through a swizzled smem tile + TMA store
+  EPI_STATS_IMG = 64, // with EPI_STATS: statistics per IMAGE (GroupNorm): stats[b][0:N] sums, stats[b][N:2N] squares;
+                      // needs one image per 128-pixel tile (TB == 1)
 };
 
 // Implicit-GEMM geometry. GEMM-M enumerates an output grid [GB, GH, GW] in tiles of [TB, TH, TW] (TB*TH*TW == 128).

@@ -26,6 +26,17 @@ __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// 16-byte packed bf16 vector <-> 8 floats (kept packed while loads are in flight to save registers)
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // Counter-based, stateless dropout RNG: a 32-bit integer hash (lowbias32) of (seed, element index); one hash yields

@@ -427,6 +427,133 @@ __global__ void __launch_bounds__(256) final_conv_tanh_fwd_kernel(const bf16* __
   }
 }
 
+// Decoder tail in ONE pass (lunar_generate.py:187-189 up4's GroupNorm + Mish, then :226-228 final conv + tanh):
+//   h = mish(gn(t))  (bf16, optionally written for the backward)   recon = tanh(conv3x3(h, w) + bias)   NCHW fp32
+// A block owns a 32 x 16 pixel tile of one image: the 34 x 18 halo of the raw transposed-conv output t is normalised and
+// activated on the way into shared memory (80-byte pixel pitch: conflict-free ldmatrix), then each warp runs
+// mma.sync m16n8k16 over 2 rows x 2 sixteen-pixel groups with K = 9 taps x 32 channels, N = 8 (3 used). The
+// normalised 32-channel tensor (the largest of the decoder) is neither written nor re-read on the sampling path.
+constexpr int kFtW = 32, kFtH = 16, kFtPitch = 80;
+__global__ void __launch_bounds__(256, 3) gn_mish_final_conv_tanh_kernel(
+    const bf16* __restrict__ t, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ w, const float* __restrict__ bias,
+    bf16* __restrict__ h_out, float* __restrict__ recon, int H, int W, int groups, float eps) {
+  constexpr int C = 32, HX = kFtW + 2, HY = kFtH + 2;
+  extern __shared__ __align__(16) unsigned char tile[];            // [HY][HX] pixels of kFtPitch bytes
+  __shared__ float2 sg[64];
+  const int b = blockIdx.z, y0 = blockIdx.y * kFtH, x0 = blockIdx.x * kFtW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tq = lane & 3;
+  const int cpg = C / groups;
+  block_group_stats(stats + (size_t)b * 2 * C, nullptr, nullptr, C, groups, 1.f / ((float)cpg * (float)H * (float)W),
+                    eps, sg);
+  // ---- phase 1: halo tile -> GroupNorm + Mish -> bf16 smem (zeros outside the image = the conv's padding)
+  {
+    const int c0 = (threadIdx.x & 3) * 8;            // 256 % 4 == 0: a thread keeps its channel octet
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 ms = sg[(c0 + j) / cpg];
+      sc[j] = gamma[c0 + j] * ms.y;
+      sh[j] = beta[c0 + j] - ms.x * sc[j];
+    }
+    constexpr int kTasks = HX * HY * 4, kBatch = 5;   // 16-byte chunks of the halo tile; kBatch loads in flight per thread
+    for (int k0 = 0; k0 * 256 < kTasks; k0 += kBatch) {
+      uint4 raw[kBatch];
+      size_t offs[kBatch];
+      int flags[kBatch];                               // bit 0: inside the image, bit 1: interior pixel of the tile
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int task = threadIdx.x + (k0 + u) * 256;
+        const int px = task >> 2, hy = px / HX, hx = px % HX;
+        const int y = y0 + hy - 1, x = x0 + hx - 1;
+        const bool in = task < kTasks && y >= 0 && y < H && x >= 0 && x < W;
+        offs[u] = (((size_t)b * H + (in ? y : 0)) * W + (in ? x : 0)) * C + c0;
+        flags[u] = (in ? 1 : 0) | ((hy >= 1 && hy <= kFtH && hx >= 1 && hx <= kFtW) ? 2 : 0);
+        raw[u] = in ? ldg16(t + offs[u]) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int task = threadIdx.x + (k0 + u) * 256;
+        if (task >= kTasks) break;
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+        if (flags[u] & 1) {
+          float v[8];
+          unpack8(raw[u], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = mish_f(v[j] * sc[j] + sh[j]);
+          __nv_bfloat162 p2[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          packed = *reinterpret_cast<uint4*>(p2);
+          if (h_out != nullptr && (flags[u] & 2)) *reinterpret_cast<uint4*>(h_out + offs[u]) = packed;
+        }
+        *reinterpret_cast<uint4*>(tile + (task >> 2) * kFtPitch + c0 * 2) = packed;
+      }
+    }
+  }
+  // B fragment of (tap, k-half): b0 = W[k = 2t, 2t+1][n = g], b1 = W[k = 2t+8, 2t+9][n = g]; n >= 3 is zero padding
+  uint32_t bfrag[9][2][2];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float w0 = 0.f, w1 = 0.f;
+        if (g < 3) {
+          const int ci = kh * 16 + r * 8 + 2 * tq;
+          w0 = w[(g * 32 + ci) * 9 + tap];          // reference layout [o][ci][kh][kw]
+          w1 = w[(g * 32 + ci + 1) * 9 + tap];
+        }
+        __nv_bfloat162 p = __floats2bfloat162_rn(w0, w1);
+        bfrag[tap][kh][r] = *reinterpret_cast<uint32_t*>(&p);
+      }
+  const float b_lo = (2 * tq < 3) ? bias[2 * tq] : 0.f, b_hi = (2 * tq + 1 < 3) ? bias[2 * tq + 1] : 0.f;
+  __syncthreads();
+  // ---- phase 2: warp w -> tile rows 2w, 2w+1; per row two 16-pixel M tiles
+  const uint32_t tile_base = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+  const int mat = lane >> 3;                                      // ldmatrix.x4: matrix fed by this lane's address
+  const int lpix = (lane & 7) + ((mat & 1) ? 8 : 0), lch = (mat >> 1) ? 8 : 0;
+  const long hw = (long)H * W;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = warp * 2 + rr;
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kh3 = 0; kh3 < 3; ++kh3)
+#pragma unroll
+        for (int kw3 = 0; kw3 < 3; ++kw3) {
+          const uint32_t pix_addr = tile_base + ((r + kh3) * HX + cb * 16 + kw3 + lpix) * kFtPitch + lch * 2;
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            uint32_t a[4];
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                         : "r"(pix_addr + kh * 32));
+            asm volatile(
+                "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                "{%0, %1, %2, %3};"
+                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[kh3 * 3 + kw3][kh][0]),
+                  "r"(bfrag[kh3 * 3 + kw3][kh][1]));
+          }
+        }
+      // C fragment: d[0], d[1] = (pixel g, outputs 2t, 2t+1); d[2], d[3] = (pixel g+8, same outputs)
+      float* obase = recon + (long)b * 3 * hw + (long)(y0 + r) * W + x0 + cb * 16;
+      if (2 * tq < 3) {
+        obase[(2 * tq) * hw + g] = tanhf(rbf(d[0] + b_lo));
+        obase[(2 * tq) * hw + g + 8] = tanhf(rbf(d[2] + b_lo));
+      }
+      if (2 * tq + 1 < 3) {
+        obase[(2 * tq + 1) * hw + g] = tanhf(rbf(d[1] + b_hi));
+        obase[(2 * tq + 1) * hw + g + 8] = tanhf(rbf(d[3] + b_hi));
+      }
+    }
+  }
+}
+
 // dx[b,h,w,ci] = sum_{o,taps} dpre[b,o,h+1-kh,w+1-kw] * w[o][ci][kh][kw],  dpre = drecon * (1 - recon^2)
 __global__ void __launch_bounds__(256) final_conv_dgrad_kernel(const float* __restrict__ drecon,
                                                                const float* __restrict__ recon,
@@ -702,6 +829,25 @@ int lun_final_conv_tanh_fwd(const void* x, const float* w, const float* bias, fl
   long blocks = (groups + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   final_conv_tanh_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, recon, B, H, W);
+  lun::note_launch(1);
+  return LUN_LAUNCH_OK();
+}
+
+int lun_gn_mish_final_conv_tanh_fwd(const void* t, const float* stats, const float* gamma, const float* beta,
+                                    const float* w, const float* bias, void* h_out, float* recon, int B, int H, int W,
+                                    int groups, float eps, void* stream) {
+  if (W % kFtW || H % kFtH || 32 % groups) return LUN_E_SHAPE;
+  dim3 grid(W / kFtW, H / kFtH, B);
+  const int smem = (kFtW + 2) * (kFtH + 2) * kFtPitch;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gn_mish_final_conv_tanh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return LUN_E_ATTR;
+    configured = true;
+  }
+  gn_mish_final_conv_tanh_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)t, stats, gamma, beta, w, bias,
+                                                                         (bf16*)h_out, recon, H, W, groups, eps);
   lun::note_launch(1);
   return LUN_LAUNCH_OK();
 }

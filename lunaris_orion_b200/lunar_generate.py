@@ -251,6 +251,18 @@ def _nchw_cols_to_nhwc(w, C=512, S=64):
     return w.view(n, C, S).permute(0, 2, 1).reshape(n, C * S)
 
 
+def _conv_gn(B, hw, C, dev, conv_fn):
+    """Run a conv whose output feeds a GroupNorm. conv_fn(img_stats) -> [B,hw,hw,C] bf16. Returns (t [B,HW,C], per-image
+    channel sums [B,2,C]): accumulated by the conv epilogue itself when an image holds >= 128 output pixels (one
+    image per tile), by a separate pass over t otherwise."""
+    HW = hw * hw
+    if ops.img_stats_ok(hw, hw):
+        st = torch.zeros(B, 2, C, device=dev, dtype=torch.float32)
+        return conv_fn(st).view(B, HW, C), st
+    t = conv_fn(None).view(B, HW, C)
+    return t, _gn_stats(t, B, HW, C)
+
+
 def _gn_stats(t, B, HW, C):
     st = torch.zeros(B, 2, C, device=t.device, dtype=torch.float32)
     check(_capi.lib().lun_image_channel_stats_bf16(t.data_ptr(), st.data_ptr(), B, HW, C, _stream()),
@@ -292,11 +304,11 @@ def _resblock_forward(rb, a, B, hw, C, save):
     HW = hw * hw
     c1, g1 = rb.conv1[0], rb.conv1[1]
     c2, g2 = rb.conv2[0], rb.conv2[1]
-    t1 = ops.conv2d_fprop(a.view(B, hw, hw, C), _wfwd(c1), 3, 1, 1, bias=_f32(c1.bias)).view(B, HW, C)
-    s1 = _gn_stats(t1, B, HW, C)
+    t1, s1 = _conv_gn(B, hw, C, a.device, lambda st: ops.conv2d_fprop(a.view(B, hw, hw, C), _wfwd(c1), 3, 1, 1,
+                                                                      bias=_f32(c1.bias), img_stats=st))
     r1 = _gn_mish(t1, s1, g1, B, HW, C)
-    t2 = ops.conv2d_fprop(r1.view(B, hw, hw, C), _wfwd(c2), 3, 1, 1, bias=_f32(c2.bias)).view(B, HW, C)
-    s2 = _gn_stats(t2, B, HW, C)
+    t2, s2 = _conv_gn(B, hw, C, a.device, lambda st: ops.conv2d_fprop(r1.view(B, hw, hw, C), _wfwd(c2), 3, 1, 1,
+                                                                      bias=_f32(c2.bias), img_stats=st))
     out = _gn_mish(t2, s2, g2, B, HW, C, res=a)
     return out, (dict(a=a, t1=t1, s1=s1, r1=r1, t2=t2, s2=s2) if save else None)
 
@@ -319,10 +331,10 @@ def _encoder_forward(enc, x, save):
             t0 = torch.empty(B, HW, C, device=x.device, dtype=torch.bfloat16)
             check(lib.lun_conv3x3_c3_fwd(x.data_ptr(), _f32(conv.weight).data_ptr(), _f32(conv.bias).data_ptr(),
                                          t0.data_ptr(), B, H, W, C, 2, _stream()), "lun_conv3x3_c3_fwd")
+            s0 = _gn_stats(t0, B, HW, C)
         else:
-            t0 = ops.conv2d_fprop(h.view(B, hw * 2, hw * 2, chans[i - 1]), _wfwd(conv), 3, 2, 1,
-                                  bias=_f32(conv.bias)).view(B, HW, C)
-        s0 = _gn_stats(t0, B, HW, C)
+            t0, s0 = _conv_gn(B, hw, C, x.device, lambda st, h=h, i=i: ops.conv2d_fprop(
+                h.view(B, hw * 2, hw * 2, chans[i - 1]), _wfwd(conv), 3, 2, 1, bias=_f32(conv.bias), img_stats=st))
         a = _gn_mish(t0, s0, gn, B, HW, C)
         out, rsv = _resblock_forward(rb, a, B, hw, C, save)
         if save:
@@ -356,20 +368,30 @@ def _decoder_forward(dec, z, skips, save):
         up = getattr(dec, f"up{i + 1}")
         convT, gn = up[0], up[1]
         cin, C = chans[i], chans[i + 1]
-        t = ops.convT4x4s2_fprop(h.view(B, hw, hw, cin), _wT(convT), bias=_f32(convT.bias))
+        if ops.img_stats_ok(hw, hw):               # each output phase grid is hw x hw per image
+            st = torch.zeros(B, 2, C, device=z.device, dtype=torch.float32)
+            t = ops.convT4x4s2_fprop(h.view(B, hw, hw, cin), _wT(convT), bias=_f32(convT.bias), img_stats=st)
+        else:
+            st = None
+            t = ops.convT4x4s2_fprop(h.view(B, hw, hw, cin), _wT(convT), bias=_f32(convT.bias))
         hw *= 2
         HW = hw * hw
         t = t.view(B, HW, C)
-        st = _gn_stats(t, B, HW, C)
+        if st is None:
+            st = _gn_stats(t, B, HW, C)
         add = skips[2 - i] if (i < 3 and len(skips) >= 3 - i) else None
-        out = _gn_mish(t, st, gn, B, HW, C, add=add)
         if save:
             saved.append(dict(inp=h, t=t, st=st, hw=hw, C=C, cin=cin, has_skip=add is not None))
-        h = out
+        if i == 3:
+            break                                   # up4's GroupNorm + Mish is fused into the final conv below
+        h = _gn_mish(t, st, gn, B, HW, C, add=add)
     fc = dec.final_conv
     recon = torch.empty(B, 3, hw, hw, device=z.device, dtype=torch.float32)
-    check(lib.lun_final_conv_tanh_fwd(h.data_ptr(), _f32(fc.weight).data_ptr(), _f32(fc.bias).data_ptr(),
-                                      recon.data_ptr(), B, hw, hw, _stream()), "lun_final_conv_tanh_fwd")
+    h = torch.empty_like(t) if save else None       # the normalised 32-channel tensor exists only for the backward
+    check(lib.lun_gn_mish_final_conv_tanh_fwd(t.data_ptr(), st.data_ptr(), _f32(gn.weight).data_ptr(),
+                                              _f32(gn.bias).data_ptr(), _f32(fc.weight).data_ptr(),
+                                              _f32(fc.bias).data_ptr(), _p(h), recon.data_ptr(), B, hw, hw,
+                                              gn.num_groups, gn.eps, _stream()), "lun_gn_mish_final_conv_tanh_fwd")
     return recon, (dict(stages=saved, x_last=h, z=z) if save else None)
 
 

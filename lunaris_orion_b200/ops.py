@@ -9,7 +9,7 @@ import torch
 from . import _capi
 from ._capi import check, int_array
 
-EPI_BIAS, EPI_LEAKY, EPI_STATS, EPI_OUT_F32, EPI_TANH = 1, 2, 4, 8, 16
+EPI_BIAS, EPI_LEAKY, EPI_STATS, EPI_OUT_F32, EPI_TANH, EPI_STATS_IMG = 1, 2, 4, 8, 16, 64
 
 
 def _stream():
@@ -52,7 +52,7 @@ def pack_convT_weight_dgrad(w):
 
 # ------------------------------------------------------------------------------------------------ raw launchers
 def conv_taps(x, w_packed, cout, grid, in_mul, taps, out, out_hw, o_mul=1, o_ph=0, o_pw=0, o_coff=0, bias=None,
-              flags=0, slope=0.2, stats=None):
+              flags=0, slope=0.2, stats=None, img_stats=None):
     """out[b, h*o_mul+o_ph, w*o_mul+o_pw, o_coff+n] = epi(sum_t x[b, h*in_mul+dy_t, w*in_mul+dx_t, :] . w[slab_t][n])."""
     _nhwc(x)
     XB, XH, XW, cin = x.shape
@@ -66,6 +66,10 @@ def conv_taps(x, w_packed, cout, grid, in_mul, taps, out, out_hw, o_mul=1, o_ph=
     if stats is not None:
         flags |= EPI_STATS
         assert stats.dtype == torch.float32 and stats.numel() == 2 * cout
+    if img_stats is not None:                    # per-image sums for GroupNorm, accumulated into [GB, 2, cout]
+        assert stats is None and img_stats.dtype == torch.float32 and img_stats.numel() == 2 * cout * GB
+        flags |= EPI_STATS | EPI_STATS_IMG
+        stats = img_stats
     assert w_packed.dtype == torch.bfloat16 and w_packed.shape[1] == cout and w_packed.shape[2] == cin
     assert out.dtype == (torch.float32 if flags & EPI_OUT_F32 else torch.bfloat16)
     rc = _capi.lib().lun_conv_taps_bf16(
@@ -97,8 +101,13 @@ def _conv_taps_list(k, pad):
     return [(kh - pad, kw - pad, kh * k + kw) for kh in range(k) for kw in range(k)]
 
 
+def img_stats_ok(gh, gw):
+    """The fused per-image statistics need one image per 128-pixel tile of the output grid."""
+    return gh * gw >= 128
+
+
 def conv2d_fprop(x, w_packed, k, stride, pad, bias=None, act_leaky=False, stats=None, out=None, out_f32=False,
-                 slope=0.2):
+                 slope=0.2, img_stats=None):
     """F.conv2d on NHWC bf16 (lunar_evaluator.py:242; lunar_generate.py:36,95). Optional fused bias, LeakyReLU and
     per-channel batch statistics (sum, sum of squares) for the BatchNorm that follows in the reference."""
     B, H, W, _ = x.shape
@@ -108,7 +117,7 @@ def conv2d_fprop(x, w_packed, k, stride, pad, bias=None, act_leaky=False, stats=
         out = torch.empty(B, OH, OW, cout, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     flags = (EPI_LEAKY if act_leaky else 0) | (EPI_OUT_F32 if out_f32 else 0)
     return conv_taps(x, w_packed, cout, (B, OH, OW), stride, _conv_taps_list(k, pad), out, (OH, OW), bias=bias,
-                     flags=flags, slope=slope, stats=stats)
+                     flags=flags, slope=slope, stats=stats, img_stats=img_stats)
 
 
 def conv2d_dgrad(dy, w_packed_dgrad, k, stride, pad, in_hw, out=None):
@@ -154,7 +163,7 @@ def _convT_phase_taps(ph, pw):
     return [(dh, dw, kh * 4 + kw) for dh, kh in rows for dw, kw in cols]
 
 
-def convT4x4s2_fprop(x, w_packed, bias=None, out=None):
+def convT4x4s2_fprop(x, w_packed, bias=None, out=None, img_stats=None):
     """F.conv_transpose2d(k=4, s=2, p=1) as four output-phase 2x2-tap sub-convolutions (lunar_generate.py:169-187)."""
     B, H, W, _ = x.shape
     cout = w_packed.shape[1]
@@ -163,7 +172,7 @@ def convT4x4s2_fprop(x, w_packed, bias=None, out=None):
     for ph in range(2):
         for pw in range(2):
             conv_taps(x, w_packed, cout, (B, H, W), 1, _convT_phase_taps(ph, pw), out, (2 * H, 2 * W), o_mul=2,
-                      o_ph=ph, o_pw=pw, bias=bias)
+                      o_ph=ph, o_pw=pw, bias=bias, img_stats=img_stats)
     return out
 
 

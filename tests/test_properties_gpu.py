@@ -58,6 +58,34 @@ def test_conv_is_linear_and_stats_match_output(cuda_dev):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout,hw,stride", [(64, 128, 32, 2), (256, 256, 16, 1), (128, 64, 32, 1)])
+def test_per_image_statistics_of_conv_and_transposed_conv_match_output(cuda_dev, cin, cout, hw, stride):
+    """The GroupNorm statistics the conv epilogue accumulates per image (LUN_EPI_STATS_IMG) equal the per-image channel
+    sums / sums of squares of the stored bf16 output - for a strided 3x3 conv and for all four phases of a transposed
+    conv - and a grid with fewer than 128 pixels per image is refused (error code, no silent mixing of images)."""
+    Bn = 5
+    g = torch.Generator(device="cpu").manual_seed(cin + hw)
+    x = torch.randn(Bn, hw, hw, cin, generator=g).to(torch.bfloat16).to(cuda_dev)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).to(cuda_dev)
+    ohw = hw // stride
+    st = torch.zeros(Bn, 2, cout, device=cuda_dev)
+    y = ops.conv2d_fprop(x, ops.pack_conv_weight(w), 3, stride, 1, img_stats=st).float().view(Bn, ohw * ohw, cout)
+    assert torch.allclose(st[:, 0], y.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], (y * y).sum(1), rtol=1e-4, atol=1e-2)
+    wt = (torch.randn(cin, cout, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    st = torch.zeros(Bn, 2, cout, device=cuda_dev)
+    yt = ops.convT4x4s2_fprop(x, ops.pack_convT_weight(wt), img_stats=st).float().view(Bn, 4 * hw * hw, cout)
+    assert torch.allclose(st[:, 0], yt.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], (yt * yt).sum(1), rtol=1e-4, atol=1e-2)
+    ref = torch.nn.functional.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), stride=2,
+                                               padding=1).permute(0, 2, 3, 1).reshape(Bn, 4 * hw * hw, cout)
+    assert (yt - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    small = torch.randn(Bn, 8, 8, cin, generator=g).to(torch.bfloat16).to(cuda_dev)
+    with pytest.raises(_capi.LunarisB200Error):
+        ops.conv2d_fprop(small, ops.pack_conv_weight(w), 3, 1, 1, img_stats=torch.zeros(Bn, 2, cout, device=cuda_dev))
+
+
+@pytest.mark.gpu
 def test_wgrad_gram_matrix_is_symmetric_with_exact_trace(cuda_dev):
     """1x1 weight gradient with dy == x is the Gram matrix of the activations: symmetric to fp32 reduction noise and
     its trace equals sum(x^2). 3x3: the center-tap slab of dW equals that Gram matrix too."""
