@@ -250,10 +250,61 @@ def cpu_reference(a, steps, warmup, budget_s=150.0):
                       "C3 architecture, fp32, %d threads, %.1f s/step" % (Bs, torch.get_num_threads(), t_total / done)}
 
 
+def eager_gpu_reference(a):
+    """SURVEY.md 8(d) "existing kernel" bar: the reference's op sequence (oracle port, loop-free, so faster than the
+    reference's own 16k-iteration Python loop) as stock PyTorch eager kernels under bf16 autocast on this B200:
+    cuDNN / cuBLAS / ATen, no kernel of this repo. Reported beside, never instead of, the CPU reference arm."""
+    import torch
+    from oracle import restatement as R
+    from lunaris_orion_b200.lunar_evaluator import LunarMoETeacher
+    from lunaris_orion_b200.lunar_generate import LunarisCoreVAE
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.manual_seed(42)
+    vae = LunarisCoreVAE(a.latent)
+    teacher = LunarMoETeacher(feature_dim=a.feat, embedding_dim=a.emb, dropout_rate=0.0)
+
+    def leaf_sd(m):
+        sd = {k: v.detach().clone().to(dev) for k, v in m.state_dict().items()}
+        for n, _ in m.named_parameters():
+            sd[n].requires_grad_(True)
+        return sd
+    vsd, tsd = leaf_sd(vae), leaf_sd(teacher)
+    Bs = a.eager_batch
+    x = torch.rand(Bs, 3, 128, 128, device=dev) * 2 - 1
+    torch.backends.cudnn.benchmark = True
+
+    def one():
+        for sd in (vsd, tsd):
+            for v in sd.values():
+                v.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            R.train_step(x, vsd, tsd, torch.randn(Bs, a.latent, device=dev))
+    for _ in range(max(a.warmup, 2)):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    print(json.dumps({
+        "impl": "reference", "device": "cuda-eager", "metric": "train images/sec @128x128 bf16 (hybrid VAE+Teacher step)",
+        "value": round(Bs / ms * 1e3, 2), "unit": "images/s", "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 2),
+        "ms_per_step": round(ms, 2), "higher_is_better": True, "dtype": "bf16 autocast", "data": "synthetic",
+        "config": {"workload": "C3 architecture (latent %d, emb %d, feat %d), batch %d; oracle port of the reference op "
+                               "sequence (no optimizer step, no dropout RNG) on stock PyTorch eager kernels"
+                               % (a.latent, a.emb, a.feat, Bs)},
+        "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}), flush=True)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if a.ref_device == "cuda":
+        return eager_gpu_reference(a)
     cb = cpu_reference(a, steps=a.steps, warmup=min(a.warmup, 1))
     line = {
         "impl": "reference", "metric": "train images/sec @128x128 bf16 (hybrid VAE+Teacher step)",
@@ -281,6 +332,9 @@ def main():
     p.add_argument("--feat", type=int, default=CFG["feat"])
     p.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4)
     p.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    p.add_argument("--ref-device", dest="ref_device", default="cpu", choices=["cpu", "cuda"],
+                   help="--impl reference only: 'cuda' times the same op sequence as stock PyTorch eager kernels on the GPU")
+    p.add_argument("--eager-batch", dest="eager_batch", type=int, default=16)
     a = p.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -49,6 +49,15 @@ int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const voi
                        const float* bias, void* out, int OH, int OW, int o_mul, int o_ph, int o_pw, int ldo,
                        int o_coff, int flags, float slope, float* stats, void* stream);
 
+/* ConvTranspose2d(k=4, s=2, p=1) for thin stages (lunar_generate.py:181-187), all four output phases in one launch:
+ * x [B,H,W,Cin] bf16 NHWC -> out [B,2H,2W,Cout] bf16 (+ bias). A CTA loads the 18x10 halo of a 16x8 input block once
+ * per 64-channel chunk and reads every tap shift from it through UMMA descriptor offsets; weights stay resident.
+ * w_packed: [16][Cout][Cin] bf16 (slab kh*4+kw); img_stats: optional fp32 [B][2][Cout] per-image sums / sums of
+ * squares of the stored output (GroupNorm), accumulated with atomics. H % 16 == 0, W % 8 == 0, Cin % 64 == 0,
+ * Cout in {32, 64}. */
+int lun_convT4x4s2_halo_bf16(const void* x, int B, int H, int W, int Cin, const void* w_packed, int Cout,
+                             const float* bias, void* out, float* img_stats, void* stream);
+
 /* Weight gradient in tap-list form (tcgen05, MN-major operands, split-K with fp32 red.add):
  *   dw[slab[t]][co][ci] += sum_{(b,h,w) in [GB,GH,GW]} dy[b, h*dy_mul+dy_ph, w*dy_mul+dy_pw, co]
  *                                                     * x[b, h*in_mul+tdy[t], w*in_mul+tdx[t], ci]

@@ -4,11 +4,14 @@ Activations are NHWC bf16 contiguous tensors; packed weights are bf16 [slab][Cou
 reference's conv2d / conv_transpose2d / linear call sites (lunar_generate.py, lunar_evaluator.py) and their
 gradients into the implicit-GEMM form the kernels execute.
 """
+import os
+
 import torch
 
 from . import _capi
 from ._capi import check, int_array
 
+_HALO_CONVT = os.environ.get("LUN_CONVT_HALO", "1") != "0"   # A/B switch for the fused-phase transposed conv
 EPI_BIAS, EPI_LEAKY, EPI_STATS, EPI_OUT_F32, EPI_TANH, EPI_STATS_IMG = 1, 2, 4, 8, 16, 64
 
 
@@ -165,10 +168,19 @@ def _convT_phase_taps(ph, pw):
 
 def convT4x4s2_fprop(x, w_packed, bias=None, out=None, img_stats=None):
     """F.conv_transpose2d(k=4, s=2, p=1) as four output-phase 2x2-tap sub-convolutions (lunar_generate.py:169-187)."""
-    B, H, W, _ = x.shape
+    B, H, W, cin = x.shape
     cout = w_packed.shape[1]
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, cout, device=x.device, dtype=torch.bfloat16)
+    if cout in (32, 64) and cin % 64 == 0 and H % 16 == 0 and W % 8 == 0 and _HALO_CONVT:
+        # thin stages: all four phases in one launch from a shared-memory halo tile (csrc/convt_halo_sm100.cu)
+        _nhwc(x)
+        assert w_packed.shape[0] == 16 and w_packed.shape[2] == cin and out.is_contiguous()
+        assert img_stats is None or img_stats.numel() == 2 * cout * B
+        check(_capi.lib().lun_convT4x4s2_halo_bf16(x.data_ptr(), B, H, W, cin, w_packed.data_ptr(), cout, _ptr(bias),
+                                                   out.data_ptr(), _ptr(img_stats), _stream()),
+              "lun_convT4x4s2_halo_bf16")
+        return out
     for ph in range(2):
         for pw in range(2):
             conv_taps(x, w_packed, cout, (B, H, W), 1, _convT_phase_taps(ph, pw), out, (2 * H, 2 * W), o_mul=2,
