@@ -151,7 +151,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&bars->full[s], ph);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sa = smem_u32(smem + s * stage_bytes);
             for (int j = 0; j < taps_per_stage; ++j) {
               // tap j of the filter row reads the same A box shifted by j pixel rows (128 bytes each)

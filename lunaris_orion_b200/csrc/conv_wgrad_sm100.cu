@@ -162,7 +162,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       for (int ks = 0; ks < nk; ++ks) {
         mbar_wait(&bars->full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
           // MN-major, 128B swizzle: LBO = distance to the next 64-channel atom, SBO = 1024 (next 8-pixel group)
           const uint64_t adesc = make_smem_desc_sw128(sa, atom, 1024);

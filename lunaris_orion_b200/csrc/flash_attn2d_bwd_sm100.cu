@@ -136,7 +136,7 @@ flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       mbar_wait(&bars->yqk_full[ys], (j / nbuf) & 1);
       mbar_wait(&bars->s_empty, (j & 1) ^ 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t adesc = make_smem_desc_sw128(smem_u32(sXqk), 0, 1024);
         const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sYqk + ys * kFbTile), 0, 1024);
 #pragma unroll
@@ -152,7 +152,7 @@ flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         const int cs = (int)(g % ycst);
         mbar_wait(&bars->yc_full[cs], (g / ycst) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sXc + ch * kFbTile), 0, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sYc + cs * kFbTile), 0, 1024);
 #pragma unroll
@@ -168,7 +168,7 @@ flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       const int ys = j % nbuf;
       mbar_wait(&bars->p_full, j & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sDS + (k >> 2) * kFbTile) + (k & 3) * 32, 0, 1024);

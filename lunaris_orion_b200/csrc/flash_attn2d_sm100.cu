@@ -128,7 +128,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         mbar_wait(&bars->k_full[ks], kph);
         mbar_wait(&bars->s_empty, sph ^ 1);          // softmax warps finished reading the previous S
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + ks * kFaTileBytes), 0, 1024);
 #pragma unroll
@@ -143,7 +143,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
           mbar_wait(&bars->v_full[vsx], vph);
           mbar_wait(&bars->p_full, pph);              // P tile written by the softmax warps
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             // A = P: two K-major atoms of 64 keys (8 KB... 16 KB apart); B = V: N-major atoms 16 KB apart
 #pragma unroll
             for (int k = 0; k < 8; ++k) {

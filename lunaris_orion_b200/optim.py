@@ -26,7 +26,7 @@ class ClipAdamW(torch.optim.AdamW):
     def step(self, closure=None):
         lib = _capi.lib()
         stream = torch.cuda.current_stream().cuda_stream
-        rows, chunks, steps = [], [], []
+        rows, chunks, steps, touched = [], [], [], []
         t = None
         for group in self.param_groups:
             for p in group["params"]:
@@ -47,6 +47,7 @@ class ClipAdamW(torch.optim.AdamW):
                              p.numel()))
                 chunks += [(idx, c) for c in range((p.numel() + _CHUNK - 1) // _CHUNK)]
                 steps.append(st["step"])
+                touched.append(p)
         if not rows:
             return None
         group = self.param_groups[0]          # the trainer uses a single group per model
@@ -67,6 +68,9 @@ class ClipAdamW(torch.optim.AdamW):
                                        self.max_grad_norm, float(group["lr"]), b1, b2, group["eps"],
                                        group["weight_decay"], 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t), stream),
               "lun_multi_clip_adamw")
+        # the kernels wrote the parameters through raw pointers: tell autograd they changed in place, so every cache
+        # keyed on `param._version` (the packed bf16 kernel operands of the drop-in modules) is rebuilt next forward
+        torch.autograd.graph.increment_version(touched)
         self.last_grad_norm_sq = norm2
         self._keep = (tab_d, ch_d)                                 # keep the tables alive until the kernels ran
         return None

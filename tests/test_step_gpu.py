@@ -91,7 +91,7 @@ def test_training_makes_progress_and_stays_finite(cuda_dev, tmp_path):
     args = build_arg_parser().parse_args([
         "--data_dir", "synthetic", "--output_dir", str(tmp_path), "--batch_size", "4",
         "--gradient_accumulation_steps", "1", "--latent_dim", "64", "--embedding_dim", "32", "--feature_dim", "64",
-        "--vae_lr", "1e-3", "--seed", "7"])
+        "--seed", "7"])                              # reference default learning rates (1e-4)
     tm = TrainingManager(args, device=cuda_dev)
     x = tc.images(4, 21).to(cuda_dev)
     frozen0 = tm.teacher.experts[0][1].conv1[0].weight.detach().clone()
@@ -128,6 +128,7 @@ def test_clip_adamw_matches_torch_clip_plus_adamw(cuda_dev):
         for p, q in zip(pa, pb):
             assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), step
             assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-8), step
+            assert p._version > step, "the raw-pointer update must be visible to autograd's version counter"
     sa, sb = oa.state_dict(), ob.state_dict()
     assert sa["state"].keys() == sb["state"].keys()
     for k in sa["state"]:
@@ -136,3 +137,35 @@ def test_clip_adamw_matches_torch_clip_plus_adamw(cuda_dev):
         assert torch.allclose(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-10)
     assert set(sb["param_groups"][0].keys()) <= set(sa["param_groups"][0].keys())
     assert dead_a.grad is None and len(oa.state[dead_a]) == 0
+
+
+@pytest.mark.gpu
+def test_forward_after_an_optimizer_step_runs_on_the_updated_weights(cuda_dev, tmp_path):
+    """The kernels consume packed bf16 shadows of the fp32 parameters, cached per parameter version. After a fused
+    clip + AdamW step (which writes the parameters through raw pointers) the next forward must see the NEW weights:
+    its outputs equal those of freshly built modules loaded from the updated state_dict (to the run-to-run noise of
+    the atomically accumulated GroupNorm / BatchNorm sums), and differ clearly from the pre-step outputs."""
+    from lunaris_orion_b200 import lunar_evaluator as le, lunar_generate as lg
+    tm = _manager(cuda_dev, tmp_path)
+    x = tc.images(CFG["B"], CFG["img_seed"]).to(cuda_dev)
+
+    def outputs(vae, teacher):
+        vae.eval(), teacher.eval()
+        with torch.no_grad():
+            _, mu, _ = vae(x)
+            return mu.float().clone(), tc.logit(teacher(x)["quality_scores"])
+    mu_before, q_before = outputs(tm.vae, tm.teacher)
+    tm.vae.train(), tm.teacher.train()
+    torch.manual_seed(1)
+    tm._process_batch(x, 0)                       # forward (fills the caches) + backward + optimizer step
+    mu_live, q_live = outputs(tm.vae, tm.teacher)
+    vae2 = lg.LunarisCoreVAE(CFG["latent"]).to(cuda_dev)
+    t2 = le.LunarMoETeacher(feature_dim=CFG["feat"], embedding_dim=CFG["emb"], dropout_rate=0.0).to(cuda_dev)
+    vae2.load_state_dict(tm.vae.state_dict())
+    t2.load_state_dict(tm.teacher.state_dict(), strict=False)
+    mu_new, q_new = outputs(vae2, t2)
+    scale = mu_new.abs().max().item()
+    moved = (mu_new - mu_before).abs().max().item()
+    assert (mu_live - mu_new).abs().max().item() < 0.02 * scale, "live modules ran on stale packed weights"
+    assert moved > 0.2 * scale, "one AdamW step must move mu visibly (32768-wide fc), else this test proves nothing"
+    assert (q_live - q_new).abs().max().item() < 0.05 * (q_new.abs().max().item() + 1.0)
