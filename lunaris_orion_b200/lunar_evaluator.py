@@ -233,8 +233,7 @@ def _packed(param, kind):
     return t
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+_stream = _capi.raw_stream
 
 
 def _cpu_seed():

@@ -237,8 +237,7 @@ def _wTdgrad(convT):
     return _cached((convT.weight,), "Tdgrad", lambda: ops.pack_convT_weight_dgrad(convT.weight))
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+_stream = _capi.raw_stream
 
 
 def _p(t):

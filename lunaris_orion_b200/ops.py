@@ -15,8 +15,7 @@ _HALO_CONVT = os.environ.get("LUN_CONVT_HALO", "1") != "0"   # A/B switch for th
 EPI_BIAS, EPI_LEAKY, EPI_STATS, EPI_OUT_F32, EPI_TANH, EPI_STATS_IMG = 1, 2, 4, 8, 16, 64
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+_stream = _capi.raw_stream
 
 
 def _ptr(t):

@@ -25,7 +25,7 @@ class ClipAdamW(torch.optim.AdamW):
     @torch.no_grad()
     def step(self, closure=None):
         lib = _capi.lib()
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _capi.raw_stream()
         rows, chunks, steps, touched = [], [], [], []
         t = None
         for group in self.param_groups:

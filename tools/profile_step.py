@@ -6,8 +6,9 @@ import bench
 from lunaris_orion_b200.train_hybrid import TrainingManager
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+L, E, F = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (512, 256, 512)    # latent, emb, feat
 dev = torch.device("cuda:0")
-tm = TrainingManager(bench._args_ns(B, 512, 256, 512), device=dev)
+tm = TrainingManager(bench._args_ns(B, L, E, F), device=dev)
 x = torch.rand(B, 3, 128, 128, device=dev) * 2 - 1
 for i in range(2):
     tm._process_batch(x, i, return_tensor=True)
