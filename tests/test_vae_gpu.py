@@ -150,3 +150,31 @@ def test_self_attention2d_gamma_zero_init_gives_identity_and_only_gamma_gradient
         if name != "gamma":
             assert p.grad is not None and p.grad.abs().max().item() == 0.0, name
     assert att.gamma.grad.abs().item() > 0
+
+
+@pytest.mark.gpu
+def test_generate_and_rank_keeps_only_images_above_the_threshold(cuda_dev):
+    """SURVEY 8 f3 scoring path (lunaris_orion_b200/scoring.py; examples/simple_generation.py:71-134): decode ==
+    LunarisCoreVAE.sample for the same latents, scores == the Teacher's eval quality mean, the loop returns at most
+    num_samples images, all at or above the threshold, best first, and an unreachable threshold returns nothing."""
+    import torch
+    from lunaris_orion_b200 import lunar_evaluator as le, lunar_generate as lg, scoring
+    torch.manual_seed(5)
+    vae = lg.LunarisCoreVAE(64).to(cuda_dev).eval()
+    teacher = le.LunarMoETeacher(feature_dim=64, embedding_dim=32).to(cuda_dev).eval()
+    torch.manual_seed(9)
+    a = vae.sample(4)
+    torch.manual_seed(9)
+    z = torch.randn(4, 64, device=cuda_dev)
+    b = scoring.decode(vae, z)
+    assert (a - b).abs().max().item() < 2e-2                      # same kernels; GroupNorm sums are atomically ordered
+    s = scoring.assess_quality(teacher, b)
+    with torch.no_grad():
+        ref = teacher(b)["quality_scores"].mean(1, keepdim=True)
+    assert s.shape == (4, 1) and (s - ref).abs().max().item() < 2e-2 and not teacher.training
+    thr = float(s.median())
+    imgs, sc = scoring.generate_and_rank(vae, teacher, num_samples=6, quality_threshold=thr - 0.2, max_attempts=2, seed=3)
+    assert 0 < imgs.shape[0] <= 6 and imgs.shape[1:] == (3, 128, 128) and sc.shape == (imgs.shape[0], 1)
+    assert bool((sc >= thr - 0.2).all()) and bool((sc[:-1] >= sc[1:]).all())
+    none, _ = scoring.generate_and_rank(vae, teacher, num_samples=2, quality_threshold=1.5, max_attempts=1, seed=3)
+    assert none.shape[0] == 0
