@@ -191,6 +191,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = q * 32 + lane;      // accumulator row == pixel index inside the tile
     const bool do_stats = g.flags & EPI_STATS, out_f32 = g.flags & EPI_OUT_F32, tma_out = g.flags & EPI_TMA_STORE;
     const bool stats_img = g.flags & EPI_STATS_IMG;
+    const bool col_stats = (g.flags & EPI_COL_STATS) && tma_out;   // sums read back from the staged tile
     const float slope = (g.flags & EPI_LEAKY) ? g.slope : 1.f;
     const bool half_leader = (threadIdx.x == 64 + half * 128);
     const uint32_t stg_base = smem_u32(s_stage) + half * 8192;
@@ -212,6 +213,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int lw = row % g.TW, lh = (row / g.TW) % g.TH, lb = row / (g.TW * g.TH);
       const int gb = tb * g.TB + lb, gh = th * g.TH + lh, gw = tw * g.TW + lw;
       const bool valid = gb < g.GB;
+      const int rows_left = (g.GB - tb * g.TB) * g.TW * g.TH;     // rows of this tile that lie inside the batch
+      const int nvalid = rows_left < 128 ? rows_left : 128;
       const size_t pix = (static_cast<size_t>(gb) * g.OH + (gh * g.o_mul + g.o_ph)) * g.OW + (gw * g.o_mul + g.o_pw);
       const size_t obase = pix * g.ldo + g.o_coff + n_blk * block_n;
 
@@ -273,7 +276,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
           }
-          if (do_stats) {
+          if (do_stats && !col_stats) {
             // statistics of what was stored (bf16-rounded), as the reference's batch_norm sees them
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -282,7 +285,39 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
-        if (do_stats) {
+        if (do_stats && col_stats) {
+          // Column sums straight from the staged bf16 tile (what was stored): this thread owns column `lane` of the 32
+          // rows [32*rg, 32*rg+32). A warp reads one 64-byte row per load (conflict-free), and the 62-shuffle
+          // transpose-reduce of the register path is gone. The tile stays valid until the bar_b rendezvous that
+          // precedes the next chunk's writes (the TMA store only reads it).
+          const int rg = ew & 3;
+          const uint32_t col = stg_base + rg * 2048 + (lane & 7) * 2;
+          const uint32_t cj = static_cast<uint32_t>(lane) >> 3;
+          const uint32_t o0 = col + (cj << 4), o1 = col + ((cj ^ 1u) << 4), o2 = col + ((cj ^ 2u) << 4),
+                         o3 = col + ((cj ^ 3u) << 4);
+          const int left = nvalid - rg * 32;           // valid rows of this group (a ragged last batch tile)
+          float a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+          for (int i0 = 0; i0 < 32; i0 += 8) {
+            uint16_t hv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int sw = (u >> 1) & 3;             // == (row >> 1) & 3: 32*rg + i0 is a multiple of 8
+              const uint32_t addr = (sw == 0 ? o0 : sw == 1 ? o1 : sw == 2 ? o2 : o3) + (i0 + u) * 64;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv[u]) : "r"(addr) : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float f = i0 + u < left ? __uint_as_float(static_cast<uint32_t>(hv[u]) << 16) : 0.f;
+              a1 += f;
+              a2 = fmaf(f, f, a2);
+            }
+          }
+          float* dst = stats_img ? stats + static_cast<size_t>(tb) * 2 * g.Cout + nb + lane : &s_stats[nb + lane];
+          atomicAdd(dst, a1);
+          atomicAdd(dst + g.Cout, a2);
+        }
+        if (do_stats && !col_stats) {
           float s1[32], s2[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -471,6 +506,14 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
     g.a_reuse = ok ? 1 : 0;
   }
   // coalesced asynchronous output path: bf16, dense pixel mapping, 32-channel boxes
+  {
+    static int col_mode = -1;
+    if (col_mode < 0) {
+      const char* e = getenv("LUN_CONV_COLSTATS");
+      col_mode = e ? atoi(e) : 1;
+    }
+    if (col_mode) g.flags |= EPI_COL_STATS;
+  }
   if (!(g.flags & EPI_OUT_F32) && g.o_mul == 1)
     g.flags |= EPI_TMA_STORE;
   else

@@ -15,6 +15,7 @@ enum : int {
   EPI_STATS = 4,      // per-channel sum / sum-of-squares of the stored (rounded) values -> stats[0:N], stats[N:2N]
   EPI_OUT_F32 = 8,    // store fp32 instead of bf16
   EPI_TMA_STORE = 32, // (set by the launcher) bf16 output leaves through a swizzled smem tile + TMA store
+  EPI_COL_STATS = 128, // (set by the launcher) statistics are column sums read back from the staged output tile
   EPI_STATS_IMG = 64, // with EPI_STATS: statistics per IMAGE (GroupNorm): stats[b][0:N] sums, stats[b][N:2N] squares;
                       // needs one image per 128-pixel tile (TB == 1)
 };
