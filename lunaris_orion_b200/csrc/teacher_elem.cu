@@ -506,17 +506,35 @@ __global__ void __launch_bounds__(kEThreads) proj_expand_kernel(const bf16* __re
   const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
   if (lane_px >= g.lanes) return;
   const int b = blockIdx.y, c0 = cgi * 8;
+  // Outside the first nq rows every pixel is dropout(bf16(bias)): the kept value bf16(bias * scale) is a per-channel
+  // constant, so those rows (97 % of the tensor) cost one hash per two elements and a select - no multiply, no rounding
   float bv[8];
+  uint32_t bkeep[4];                                  // packed bf16 pairs of the kept value
 #pragma unroll
   for (int j = 0; j < 8; ++j) bv[j] = rbf(bias[c0 + j]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(thresh16 ? rbf(bv[2 * j] * drop_scale) : bv[2 * j],
+                                                   thresh16 ? rbf(bv[2 * j + 1] * drop_scale) : bv[2 * j + 1]);
+    bkeep[j] = *reinterpret_cast<const uint32_t*>(&t);
+  }
   for (int p = blockIdx.x * g.lanes + lane_px; p < HW; p += gridDim.x * g.lanes) {
     const size_t off = ((size_t)b * HW + p) * C + c0;
-    float v[8];
-    if (p < nq) load8(small + ((size_t)b * nq_pad + p) * C + c0, v);
-    else {
+    if (p >= nq) {
+      uint32_t w[4] = {bkeep[0], bkeep[1], bkeep[2], bkeep[3]};
+      if (thresh16) {
+        const uint32_t k = drop_key(seed, off >> 3);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = bv[j];
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t h = hash32(k + i);           // same stream as drop_keep8
+          w[i] = ((h & 0xFFFFu) >= thresh16 ? w[i] & 0x0000FFFFu : 0u) | ((h >> 16) >= thresh16 ? w[i] & 0xFFFF0000u : 0u);
+        }
+      }
+      *reinterpret_cast<uint4*>(y + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      continue;
     }
+    float v[8];
+    load8(small + ((size_t)b * nq_pad + p) * C + c0, v);
     if (thresh16) {
       bool keep[8];
       drop_keep8(seed, off >> 3, thresh16, keep);
