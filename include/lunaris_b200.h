@@ -222,7 +222,7 @@ int lun_flash_attn2d_bf16(const void* qk, const void* v, const void* x, void* y,
 /* Backward of the same module (what autograd derives from lunar_generate.py:70-77), three steps:
  *   prep: dsum[row] = sum_c dy[row,c] * o[row,c]; dgamma[0] += sum of all dsum (dgamma zeroed by the caller).
  *   dv:   dv[B,N,C] bf16 = gamma * P^T dy              (P rebuilt from qk and lse)
- *   dqk:  dqk[B*N,128] bf16 = gamma * [dS K | dS^T Q], dS = P o (dy v^T - dsum); two launches (queries, keys).
+ *   dqk:  dqk[B*N,128] bf16 = gamma * [dS K | dS^T Q], dS = P o (dy v^T - dsum); one launch, grid.z = {queries, keys}.
  * dy: [B, N, C] bf16 gradient of y (the residual branch dx += dy is the caller's). */
 int lun_flash_attn2d_bwd_prep_bf16(const void* dy, const void* o, float* dsum, float* dgamma, long rows, int C,
                                    void* stream);

@@ -40,13 +40,18 @@ struct __align__(16) FbBars {
   uint32_t pad;
 };
 
-// qk: [B*N, 128] bf16 = [q | k] (64 zero-padded dims each); tmX / tmY: NHWC maps of the own-side and streamed-side
-// [B, N, C] tensors (dY and V for dQ; V and dY for dK); lse, dsum: [B*N] fp32; dqk: [B*N, 128] bf16 (dq | dk).
+// qk: [B*N, 128] bf16 = [q | k] (64 zero-padded dims each); tmDY / tmV: NHWC maps of the [B, N, C] tensors (own side
+// and streamed side swap with the role); lse, dsum: [B*N] fp32; dqk: [B*N, 128] bf16 (dq | dk).
 __global__ void __launch_bounds__(kFbThreads, 1)
-flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmX,
-                        const __grid_constant__ CUtensorMap tmY, const float* __restrict__ lse,
+flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmDY,
+                        const __grid_constant__ CUtensorMap tmV, const float* __restrict__ lse,
                         const float* __restrict__ dsum, const float* __restrict__ gamma,
-                        __nv_bfloat16* __restrict__ dqk, int N, int C, int own_is_key, int nbuf, int ycst) {
+                        __nv_bfloat16* __restrict__ dqk, int N, int C, int nbuf, int ycst) {
+  // blockIdx.z selects the role, so both gradients share one launch (twice the CTAs: small N x B grids fill the GPU):
+  //   z = 0: dQ - own = queries with dY resident, V streamed;   z = 1: dK - own = keys with V resident, dY streamed
+  const int own_is_key = blockIdx.z;
+  const CUtensorMap* tmXp = own_is_key ? &tmV : &tmDY;
+  const CUtensorMap* tmYp = own_is_key ? &tmDY : &tmV;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nch = C / 64;
@@ -65,8 +70,8 @@ flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQK);
-    prefetch_tmap(&tmX);
-    prefetch_tmap(&tmY);
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmV);
     mbar_init(&bars->x_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->yqk_full[i], 1);
@@ -103,7 +108,7 @@ flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       const long row0 = (long)b * N;
       mbar_expect_tx(&bars->x_full, (1 + nch) * kFbTile);
       tma_load_2d(sXqk, &tmQK, &bars->x_full, own_col, (int)(row0 + t * 128));
-      for (int ch = 0; ch < nch; ++ch) tma_load_4d(sXc + ch * kFbTile, &tmX, &bars->x_full, ch * 64, t * 128, 0, b);
+      for (int ch = 0; ch < nch; ++ch) tma_load_4d(sXc + ch * kFbTile, tmXp, &bars->x_full, ch * 64, t * 128, 0, b);
       long g = 0;                                   // running chunk counter of the Yc ring
       for (int j = 0; j < ntiles; ++j) {
         // the order mirrors the MMA warp's (see there): with a single Yqk buffer the chunks of tile j must not wait
@@ -119,7 +124,7 @@ flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
               const int cs = (int)(g % ycst);
               mbar_wait(&bars->yc_empty[cs], ((g / ycst) & 1) ^ 1);
               mbar_expect_tx(&bars->yc_full[cs], kFbTile);
-              tma_load_4d(sYc + cs * kFbTile, &tmY, &bars->yc_full[cs], ch * 64, j * 128, 0, b);
+              tma_load_4d(sYc + cs * kFbTile, tmYp, &bars->yc_full[cs], ch * 64, j * 128, 0, b);
             }
           }
         }
@@ -225,12 +230,14 @@ flash_attn2d_bwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
+          // exp(s - lse) = exp2(s * log2e - lse * log2e): one FFMA + one MUFU.EX2 per score
+          constexpr float kLog2e = 1.4426950408889634f;
           float4 l = make_float4(lse_r, lse_r, lse_r, lse_r);
           if (own_is_key) l = __ldg(lse_t + c * 8 + i4);
-          r[c][i4 * 4 + 0] = __float_as_uint(__expf(__uint_as_float(r[c][i4 * 4 + 0]) - l.x));
-          r[c][i4 * 4 + 1] = __float_as_uint(__expf(__uint_as_float(r[c][i4 * 4 + 1]) - l.y));
-          r[c][i4 * 4 + 2] = __float_as_uint(__expf(__uint_as_float(r[c][i4 * 4 + 2]) - l.z));
-          r[c][i4 * 4 + 3] = __float_as_uint(__expf(__uint_as_float(r[c][i4 * 4 + 3]) - l.w));
+          r[c][i4 * 4 + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[c][i4 * 4 + 0]), kLog2e, -l.x * kLog2e)));
+          r[c][i4 * 4 + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[c][i4 * 4 + 1]), kLog2e, -l.y * kLog2e)));
+          r[c][i4 * 4 + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[c][i4 * 4 + 2]), kLog2e, -l.z * kLog2e)));
+          r[c][i4 * 4 + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[c][i4 * 4 + 3]), kLog2e, -l.w * kLog2e)));
         }
       const int buf = j & 1;
       mbar_wait(&bars->dp_full[buf], (j >> 1) & 1);
@@ -381,13 +388,10 @@ int lun_flash_attn2d_dqk_bf16(const void* qk, const void* v, const void* dy, con
       return LUN_E_ATTR;
     configured = true;
   }
-  dim3 grid(N / 128, B);
-  // dQ: own = queries with dY resident, V streamed;  dK: own = keys with V resident, dY streamed
+  dim3 grid(N / 128, B, 2);                  // z: dQ / dK
   flash_attn2d_bwd_kernel<<<grid, kFbThreads, smem, (cudaStream_t)stream>>>(
-      tmQK, tmDY, tmV, lse, dsum, gamma, (__nv_bfloat16*)dqk, N, C, 0, nbuf, ycst);
-  flash_attn2d_bwd_kernel<<<grid, kFbThreads, smem, (cudaStream_t)stream>>>(
-      tmQK, tmV, tmDY, lse, dsum, gamma, (__nv_bfloat16*)dqk, N, C, 1, nbuf, ycst);
-  lun::note_launch(2);
+      tmQK, tmDY, tmV, lse, dsum, gamma, (__nv_bfloat16*)dqk, N, C, nbuf, ycst);
+  lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 

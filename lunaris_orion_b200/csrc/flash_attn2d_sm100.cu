@@ -1,13 +1,17 @@
 // Global spatial self-attention for SelfAttention2d (lunar_generate.py:56-78) as a flash-style tcgen05 kernel:
 //   energy[i,j] = q_i . k_j (no scaling), attention = softmax_j, out_i = sum_j attention[i,j] v_j,  y = gamma*out + x
-// with q,k of width DQK = C/8 (zero-padded to a multiple of 16) and v of width C. The N x N matrix never exists.
+// with q,k of width DQK = C/8 (zero-padded to 64) and v of width C. The N x N matrix never exists.
 //
-// One CTA owns 128 queries and a slice of <= 256 value channels. Because DQK is 8x narrower than the value width,
-// Q K^T is cheap next to P V, so the softmax is done in TWO passes instead of rescaling the TMEM accumulator:
-//   pass A: S = Q K_j^T per 128-key tile (tcgen05, TMEM) -> running row max / row sum in registers
-//   pass B: S again, P = exp(S - max) / sum -> bf16 -> 128B-swizzled smem tile -> O += P V_j (tcgen05, O in TMEM)
+// One CTA owns 128 queries and a slice of <= 256 value channels. Q K^T is 8x cheaper than P V, so the row maximum is
+// found in a first pass over the keys (S only - no exponentials) instead of rescaling the TMEM accumulator:
+//   pass A: S = Q K_j^T per 128-key tile (tcgen05, TMEM)  -> running row max in registers
+//   pass B: S again, P = exp(S - max) UNNORMALISED -> bf16 -> 128B-swizzled smem tile -> O += P V_j (O in TMEM),
+//           row sums of P accumulated alongside; the epilogue divides O by them.
+// The SFU does one exponential per score (pass B only) and everything overlaps: S is double buffered in TMEM, so the
+// MMA warp computes S_{j+1} and runs P_j V_j while the 16 softmax warps (four per TMEM lane quarter, 32 score columns
+// each) are still exponentiating.
 // Warp roles: warp 0 = TMA producer (Q once, K / V tiles through mbarrier rings), warp 1 = MMA issuer,
-// warps 2..5 = softmax + epilogue (each thread owns one query row: TMEM lane == row).
+// warps 2..17 = softmax + epilogue (thread = query row = TMEM lane; the four warps of a quarter split the columns).
 // K tiles are [128 keys][64 (padded) dims] K-major; V tiles are [128 keys][64-channel atoms] N-major (MN-major B
 // operand straight from the NHWC tensor); P is the K-major A operand of the second GEMM.
 //
@@ -26,18 +30,19 @@ int make_tmap_2d(CUtensorMap* m, const void* base, long rows, long cols, int box
 int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b,
                    int estride);
 
-constexpr int kFaThreads = 192;
+constexpr int kFaThreads = 576;           // TMA warp, MMA warp, 16 softmax warps
 constexpr int kFaTileBytes = 128 * 128;   // 128 rows x 64 bf16
 
 struct __align__(16) FaBars {
   uint64_t q_full;
   uint64_t k_full[2], k_empty[2];
   uint64_t v_full[2], v_empty[2];
-  uint64_t s_full, s_empty;      // S accumulator (TMEM) MMA -> softmax -> MMA
-  uint64_t p_full, p_empty;      // P tile (smem) softmax -> MMA
-  uint64_t o_full;               // all PV MMAs done
+  uint64_t s_full[2], s_empty[2];   // S accumulators (TMEM) MMA -> softmax -> MMA
+  uint64_t p_full[2], p_empty[2];   // P tile (smem) softmax -> MMA, one pair per 64-key atom (= per softmax warp half)
+  uint64_t o_full;                  // all PV MMAs done
   uint32_t tmem_base;
   uint32_t pad;
+  float xch[4][128];                // row statistics exchanged between the four warps of a lane quarter
 };
 
 // qk: [B*N, 128] bf16 rows = [q (64, zero padded) | k (64, zero padded)];  v: [B, N, C] bf16;  x, y: [B, N, C] bf16
@@ -60,8 +65,9 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
   const int ntiles = N / 128;
   const uint32_t tmem_cols = 512;
   const bool dv_mode = lse_in != nullptr;           // backward: own tile = keys (qk columns 64..127), streamed = queries
-  const int first_pass = dv_mode ? 1 : 0;
   const int own_col = dv_mode ? 64 : 0, other_col = dv_mode ? 0 : 64;
+  const int steps = dv_mode ? ntiles : 2 * ntiles;  // S tiles computed: pass A (forward only) then pass B
+  const int first_b = steps - ntiles;               // first step of pass B
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQK);
@@ -72,11 +78,11 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->v_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->s_empty[i], 16);
+      mbar_init(&bars->p_full[i], 8);
+      mbar_init(&bars->p_empty[i], 1);
     }
-    mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->s_empty, 4);
-    mbar_init(&bars->p_full, 4);
-    mbar_init(&bars->p_empty, 1);
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
   }
@@ -88,8 +94,8 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const uint32_t tmem_s = tmem_base;                // 128 columns: S
-  const uint32_t tmem_o = tmem_base + 128;          // vw (<= 256) columns: O
+  const uint32_t tmem_s = tmem_base;                // 2 x 128 columns: S double buffer
+  const uint32_t tmem_o = tmem_base + 256;          // vw (<= 256) columns: O
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -97,22 +103,19 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       const long row0 = (long)b * N;
       mbar_expect_tx(&bars->q_full, kFaTileBytes);
       tma_load_2d(sQ, &tmQK, &bars->q_full, own_col, (int)(row0 + qt * 128));
-      int ks = 0, vsx = 0;
-      uint32_t kph = 0, vph = 0;
-      for (int pass = first_pass; pass < 2; ++pass) {
-        for (int j = 0; j < ntiles; ++j) {
-          mbar_wait(&bars->k_empty[ks], kph ^ 1);
-          mbar_expect_tx(&bars->k_full[ks], kFaTileBytes);
-          tma_load_2d(sK + ks * kFaTileBytes, &tmQK, &bars->k_full[ks], other_col, (int)(row0 + j * 128));
-          if (++ks == 2) { ks = 0; kph ^= 1; }
-          if (pass == 1) {
-            mbar_wait(&bars->v_empty[vsx], vph ^ 1);
-            mbar_expect_tx(&bars->v_full[vsx], vatoms * kFaTileBytes);
-            for (int a = 0; a < vatoms; ++a)
-              tma_load_4d(sV + (vsx * vatoms + a) * kFaTileBytes, &tmV, &bars->v_full[vsx], vs * vw + a * 64, j * 128,
-                          0, b);
-            if (++vsx == 2) { vsx = 0; vph ^= 1; }
-          }
+      for (int t = 0; t < steps; ++t) {
+        const int j = t < first_b ? t : t - first_b;
+        const int ks = t & 1;
+        mbar_wait(&bars->k_empty[ks], ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(&bars->k_full[ks], kFaTileBytes);
+        tma_load_2d(sK + ks * kFaTileBytes, &tmQK, &bars->k_full[ks], other_col, (int)(row0 + j * 128));
+        if (t >= first_b) {
+          const int vsx = j & 1;
+          mbar_wait(&bars->v_empty[vsx], ((j >> 1) & 1) ^ 1);
+          mbar_expect_tx(&bars->v_full[vsx], vatoms * kFaTileBytes);
+          for (int a = 0; a < vatoms; ++a)
+            tma_load_4d(sV + (vsx * vatoms + a) * kFaTileBytes, &tmV, &bars->v_full[vsx], vs * vw + a * 64, j * 128, 0,
+                        b);
         }
       }
     }
@@ -121,136 +124,144 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     const uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);   // S = Q K^T      (both K-major)
     const uint32_t idesc_o = make_idesc_bf16(128, vw, false, true);     // O += P V       (A K-major, B N-major)
     mbar_wait(&bars->q_full, 0);
-    int ks = 0, vsx = 0;
-    uint32_t kph = 0, vph = 0, sph = 0, pph = 0;
-    for (int pass = first_pass; pass < 2; ++pass) {
-      for (int j = 0; j < ntiles; ++j) {
-        mbar_wait(&bars->k_full[ks], kph);
-        mbar_wait(&bars->s_empty, sph ^ 1);          // softmax warps finished reading the previous S
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + ks * kFaTileBytes), 0, 1024);
+    auto issue_s = [&](int t) {                      // S_t into TMEM buffer t & 1
+      const int ks = t & 1;
+      mbar_wait(&bars->k_full[ks], (t >> 1) & 1);
+      mbar_wait(&bars->s_empty[ks], ((t >> 1) & 1) ^ 1);   // the softmax warps finished reading this buffer
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + ks * kFaTileBytes), 0, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(&bars->k_empty[ks]);
-          umma_commit(&bars->s_full);
-        }
-        __syncwarp();
-        if (++ks == 2) { ks = 0; kph ^= 1; }
-        sph ^= 1;
-        if (pass == 1) {
-          mbar_wait(&bars->v_full[vsx], vph);
-          mbar_wait(&bars->p_full, pph);              // P tile written by the softmax warps
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s + ks * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(&bars->k_empty[ks]);
+        umma_commit(&bars->s_full[ks]);
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int t = 0; t < steps; ++t) {
+      if (t + 1 < steps) issue_s(t + 1);             // runs under the softmax of tile t
+      if (t >= first_b) {
+        const int j = t - first_b, vsx = j & 1;
+        mbar_wait(&bars->v_full[vsx], (j >> 1) & 1);
+        // The P hand-off is per 64-key atom: while the MMAs of atom 1 run, the warps of atom 0 already store the next
+        // tile's probabilities, so the tensor pipe does not idle across the store -> fence -> barrier round trip.
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          mbar_wait(&bars->p_full[a], j & 1);        // this atom of P written by its four softmax warps
           tc_fence_after();
           if (elect_one()) {
-            // A = P: two K-major atoms of 64 keys (8 KB... 16 KB apart); B = V: N-major atoms 16 KB apart
+            // A = P atom a: K-major, 64 keys; B = V rows 64a..64a+63: N-major atoms 16 KB apart
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + (k >> 2) * kFaTileBytes) + (k & 3) * 32, 0, 1024);
+            for (int k = 4 * a; k < 4 * a + 4; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + a * kFaTileBytes) + (k & 3) * 32, 0, 1024);
               const uint64_t bdesc =
                   make_smem_desc_sw128(smem_u32(sV + vsx * vatoms * kFaTileBytes) + k * 2048, kFaTileBytes, 1024);
               umma_bf16(tmem_o, adesc, bdesc, idesc_o, (j | k) != 0);
             }
-            umma_commit(&bars->v_empty[vsx]);
-            umma_commit(&bars->p_empty);
-            if (j == ntiles - 1) umma_commit(&bars->o_full);
+            umma_commit(&bars->p_empty[a]);
+            if (a == 1) {
+              umma_commit(&bars->v_empty[vsx]);
+              if (j == ntiles - 1) umma_commit(&bars->o_full);
+            }
           }
           __syncwarp();
-          if (++vsx == 2) { vsx = 0; vph ^= 1; }
-          pph ^= 1;
         }
+        __syncwarp();
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax + epilogue (warps 2..5)
-    const int q = warp & 3;
+    // ------------------------------------------------------------ softmax + epilogue (warps 2..17)
+    const int q = warp & 3;                         // TMEM lane quarter
+    const int cq = (warp - 2) >> 2;                 // column quarter (32 of the 128 scores of a row) of the S tile
+    const int hf = cq >> 1;                         // P atom (64 keys) this warp writes into
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float m = -3.0e38f, l = 0.f;
-    uint32_t sph = 0, peph = 0;
-    // pass A: row max and row sum (the backward reads the saved statistics instead)
-    for (int j = 0; j < (dv_mode ? 0 : ntiles); ++j) {
-      mbar_wait(&bars->s_full, sph);
-      sph ^= 1;
+    // pass A: row max of this warp's 64 columns (no exponentials)
+    for (int t = 0; t < first_b; ++t) {
+      const int sb = t & 1;
+      mbar_wait(&bars->s_full[sb], (t >> 1) & 1);
       tc_fence_after();
-      float tmax = -3.0e38f;
-      uint32_t r[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + lane_addr + c * 32, r[c]);
+      uint32_t r[32];
+      tmem_ld32(tmem_s + sb * 128 + lane_addr + cq * 32, r);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty);
+      if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(r[c][i]));
-      const float mn = fmaxf(m, tmax);
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s += __expf(__uint_as_float(r[c][i]) - mn);
-      l = l * __expf(m - mn) + s;
-      m = mn;
+      for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
     }
-    const float inv_l = dv_mode ? 1.f : 1.f / l;
+    if (!dv_mode) {                                 // combine the four column quarters of every row
+      bars->xch[cq][row] = m;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      m = fmaxf(fmaxf(bars->xch[0][row], bars->xch[1][row]), fmaxf(bars->xch[2][row], bars->xch[3][row]));
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // xch is reused for the row sums
+    }
     // pass B: P tiles
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(&bars->s_full, sph);
-      sph ^= 1;
+      const int t = first_b + j, sb = t & 1;
+      mbar_wait(&bars->s_full[sb], (t >> 1) & 1);
       tc_fence_after();
-      uint32_t r[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + lane_addr + c * 32, r[c]);
+      uint32_t r[32];
+      tmem_ld32(tmem_s + sb * 128 + lane_addr + cq * 32, r);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty);
-      mbar_wait(&bars->p_empty, peph ^ 1);           // previous P consumed by the PV MMAs
-      peph ^= 1;
-      // row `row` of P: 128 keys -> two 64-key atoms, 8 chunks of 16 bytes each, chunk index swizzled by row & 7
-      const float4* lse_t = reinterpret_cast<const float4*>(lse_in + (size_t)b * N + j * 128);   // dv_mode only
+      if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
+      // this thread's 32 keys = half of atom hf of the P tile: 4 chunks of 16 bytes, chunk index swizzled by row & 7
+      const float4* lse_t = reinterpret_cast<const float4*>(lse_in + (size_t)b * N + j * 128 + cq * 32);   // dv_mode only
+      // exp(s - m) = exp2(s * log2e - m * log2e): one FFMA + one MUFU.EX2 per score
+      constexpr float kLog2e = 1.4426950408889634f;
+      const float m2 = m * kLog2e;
+      uint32_t pk[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int g = 0; g < 4; ++g) {
+        float sub[8];
+        if (dv_mode) {
+          const float4 l0 = __ldg(lse_t + g * 2), l1 = __ldg(lse_t + g * 2 + 1);
+          sub[0] = l0.x * kLog2e; sub[1] = l0.y * kLog2e; sub[2] = l0.z * kLog2e; sub[3] = l0.w * kLog2e;
+          sub[4] = l1.x * kLog2e; sub[5] = l1.y * kLog2e; sub[6] = l1.z * kLog2e; sub[7] = l1.w * kLog2e;
+        } else {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t pk[4];
-          float sub[8];
-          if (dv_mode) {
-            const float4 l0 = __ldg(lse_t + c * 8 + g * 2), l1 = __ldg(lse_t + c * 8 + g * 2 + 1);
-            sub[0] = l0.x; sub[1] = l0.y; sub[2] = l0.z; sub[3] = l0.w;
-            sub[4] = l1.x; sub[5] = l1.y; sub[6] = l1.z; sub[7] = l1.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sub[e] = m;
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 = __expf(__uint_as_float(r[c][g * 8 + 2 * e]) - sub[2 * e]) * inv_l;
-            const float p1 = __expf(__uint_as_float(r[c][g * 8 + 2 * e + 1]) - sub[2 * e + 1]) * inv_l;
-            pk[e] = pack_bf16x2(p0, p1);
-          }
-          const int key0 = c * 32 + g * 8;             // first key of this 16-byte chunk
-          const int atom = key0 >> 6, chunk = (key0 & 63) >> 3;
-          const uint32_t addr = smem_u32(sP + atom * kFaTileBytes) + row * 128 + ((chunk ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                       "r"(pk[3])
-                       : "memory");
+          for (int e = 0; e < 8; ++e) sub[e] = m2;
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(r[g * 8 + 2 * e]), kLog2e, -sub[2 * e]));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(r[g * 8 + 2 * e + 1]), kLog2e, -sub[2 * e + 1]));
+          pk[g * 4 + e] = pack_bf16x2(p0, p1);
+          l += p0 + p1;                                // row sum (the bf16 rounding of P averages out over 10^3+ keys)
+        }
+      }
+      mbar_wait(&bars->p_empty[hf], (j & 1) ^ 1);    // this atom of the previous P consumed by the PV MMAs
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int chunk = (cq & 1) * 4 + g;            // 16-byte chunk (8 keys) inside the 64-key atom
+        const uint32_t addr = smem_u32(sP + hf * kFaTileBytes) + row * 128 + ((chunk ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                     "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
+                     : "memory");
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p_full);
+      if (lane == 0) mbar_arrive(&bars->p_full[hf]);
     }
-    // epilogue: y = gamma * O + x  (backward: dV = gamma * O); training forward also keeps O and logsumexp
+    // epilogue: O / rowsum, y = gamma * O + x  (backward: dV = gamma * O); training forward also keeps O and logsumexp
+    float inv_l = 1.f;
+    if (!dv_mode) {
+      bars->xch[cq][row] = l;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      l = (bars->xch[0][row] + bars->xch[1][row]) + (bars->xch[2][row] + bars->xch[3][row]);
+      inv_l = 1.f / l;
+    }
     mbar_wait(&bars->o_full, 0);
     tc_fence_after();
     const float gm = gamma[0];
     const size_t base = ((size_t)b * N + qt * 128 + row) * C + vs * vw;
-    if (lse_out != nullptr && vs == 0) lse_out[(size_t)b * N + qt * 128 + row] = m + __logf(l);
-    for (int c0 = 0; c0 < vw; c0 += 32) {
+    if (lse_out != nullptr && vs == 0 && cq == 0) lse_out[(size_t)b * N + qt * 128 + row] = m + __logf(l);
+    for (int c0 = cq * 32; c0 < vw; c0 += 128) {    // 32-column chunks of the O slice, dealt round-robin to the 4 warps
       uint32_t r[32];
       tmem_ld32(tmem_o + lane_addr + c0, r);
       tmem_ld_wait();
@@ -265,13 +276,14 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float x0 = __uint_as_float(xw[e] << 16), x1 = __uint_as_float(xw[e] & 0xffff0000u);
-          o[e] = pack_bf16x2(gm * __uint_as_float(r[v4 * 8 + 2 * e]) + x0, gm * __uint_as_float(r[v4 * 8 + 2 * e + 1]) + x1);
+          const float o0 = __uint_as_float(r[v4 * 8 + 2 * e]) * inv_l, o1 = __uint_as_float(r[v4 * 8 + 2 * e + 1]) * inv_l;
+          o[e] = pack_bf16x2(gm * o0 + x0, gm * o1 + x1);
         }
         ys[v4] = make_uint4(o[0], o[1], o[2], o[3]);
         if (o_out != nullptr) {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            o[e] = pack_bf16x2(__uint_as_float(r[v4 * 8 + 2 * e]), __uint_as_float(r[v4 * 8 + 2 * e + 1]));
+            o[e] = pack_bf16x2(__uint_as_float(r[v4 * 8 + 2 * e]) * inv_l, __uint_as_float(r[v4 * 8 + 2 * e + 1]) * inv_l);
           reinterpret_cast<uint4*>(o_out + base + c0)[v4] = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
