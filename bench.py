@@ -27,8 +27,9 @@ sys.path.insert(0, ROOT)
 CFG = dict(batch=64, latent=512, emb=256, feat=512)
 GF_PER_IMG = 5443.3   # algorithmic GFLOP per image per step, as-executed, recompute excluded
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (3x3 512->512, B=64, production
-# epilogue) from `ncu --set full` (profiles/r01_ncu_conv_fprop_3x3_512_B64.txt); algorithmic bytes: 2.152e9
-NCU_TRAFFIC = {(512, 64): 1.091117e9 + 1.044081e9}
+# epilogue) from `ncu --set full` (profiles/r01b_ncu_conv_fprop_3x3_512_B64.txt); algorithmic bytes: 2.152e9
+NCU_TRAFFIC = {(512, 64): 1.458739e9 + 1.048327e9}
+NCU_TENSOR_PCT = {(512, 64): 95.1}     # sm__pipe_tensor_cycles_active % of elapsed, same capture (99.5 % of active)
 
 
 def _peaks():
@@ -174,7 +175,7 @@ def run_ours(a):
         roof = {"bound": "tensor", "kernel": "conv_fprop_kernel 3x3 %d->%d @128x128 B=%d (bias+LeakyReLU+BN stats)" % (C, C, B),
                 "achieved": round(fl / kms / 1e9, 1), "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if pk else "fallback",
                 "unit": "TFLOP/s", "frac": round(fl / kms / 1e9 / peak, 4), "traffic": NCU_TRAFFIC.get((C, B)),
-                "tensor_pipe_active_pct_ncu": 97.1 if (C, B) == (512, 64) else None, "ms_per_launch": round(kms, 4),
+                "tensor_pipe_active_pct_ncu": NCU_TENSOR_PCT.get((C, B)), "ms_per_launch": round(kms, 4),
                 "step_model_flop_frac_of_sustained": None}
         del x, y
 
