@@ -58,6 +58,12 @@ int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const voi
 int lun_convT4x4s2_halo_bf16(const void* x, int B, int H, int W, int Cin, const void* w_packed, int Cout,
                              const float* bias, void* out, float* img_stats, void* stream);
 
+/* ConvTranspose2d(k=4, s=2, p=1) forward, any stage (lunar_generate.py:169-187), ONE launch: the halo kernel above when
+ * its shape limits hold, otherwise the tap-list kernel with the four output phases batched as an extra work-item
+ * dimension (phase, pixel tile, channel block). Same arguments; img_stats needs H*W >= 128. */
+int lun_convT4x4s2_bf16(const void* x, int B, int H, int W, int Cin, const void* w_packed, int Cout, const float* bias,
+                        void* out, float* img_stats, void* stream);
+
 /* Weight gradient in tap-list form (tcgen05, MN-major operands, split-K with fp32 red.add):
  *   dw[slab[t]][co][ci] += sum_{(b,h,w) in [GB,GH,GW]} dy[b, h*dy_mul+dy_ph, w*dy_mul+dy_pw, co]
  *                                                     * x[b, h*in_mul+tdy[t], w*in_mul+tdx[t], ci]

@@ -38,6 +38,39 @@ int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const voi
                                 static_cast<cudaStream_t>(stream));
 }
 
+// defined in convt_halo_sm100.cu
+extern "C" int lun_convT4x4s2_halo_bf16(const void* x, int B, int H, int W, int Cin, const void* w_packed, int Cout,
+                                        const float* bias, void* out, float* img_stats, void* stream);
+
+int lun_convT4x4s2_bf16(const void* x, int B, int H, int W, int Cin, const void* w_packed, int Cout, const float* bias,
+                        void* out, float* img_stats, void* stream) {
+  // thin stages: fused-phase halo kernel; otherwise the tap-list kernel with the four phases batched into one launch
+  if ((Cout == 32 || Cout == 64) && Cin % 64 == 0 && H % 16 == 0 && W % 8 == 0)
+    return lun_convT4x4s2_halo_bf16(x, B, H, W, Cin, w_packed, Cout, bias, out, img_stats, stream);
+  lun::ConvGeom g{};
+  g.GB = B; g.GH = H; g.GW = W;
+  g.in_mul = 1;
+  g.ntaps = 4;
+  g.nphase = 4;
+  for (int p = 0; p < 4; ++p) {
+    const int ph = p >> 1, pw = p & 1;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        // output row 2j+ph gathers input rows j+dh through filter row kh: dh = ph - a, kh = (1 - ph) + 2a (same in w)
+        const int t = p * 4 + a * 2 + b;
+        g.dy[t] = ph - a;
+        g.dx[t] = pw - b;
+        g.slab[t] = ((1 - ph) + 2 * a) * 4 + (1 - pw) + 2 * b;
+      }
+  }
+  g.Cin = Cin; g.Cout = Cout;
+  g.block_n = Cout >= 256 && Cout % 256 == 0 ? 256 : Cout >= 128 && Cout % 128 == 0 ? 128 : Cout % 64 == 0 ? 64 : 32;
+  g.OH = 2 * H; g.OW = 2 * W; g.o_mul = 2; g.o_ph = 0; g.o_pw = 0; g.ldo = Cout; g.o_coff = 0;
+  g.flags = (bias ? LUN_EPI_BIAS : 0) | (img_stats ? (LUN_EPI_STATS | LUN_EPI_STATS_IMG) : 0);
+  g.slope = 1.f;
+  return lun::launch_conv_fprop(x, B, H, W, w_packed, 16, g, bias, out, img_stats, static_cast<cudaStream_t>(stream));
+}
+
 int lun_wgrad_taps_bf16(const void* dy, int YB, int YH, int YW, int Cout, int dy_mul, int dy_ph, int dy_pw,
                         const void* x, int XB, int XH, int XW, int Cin, int in_mul, int GB, int GH, int GW,
                         int ntaps, const int* tdy, const int* tdx, const int* slab, float* dw, void* stream) {

@@ -63,7 +63,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int n_blocks = g.Cout / block_n;
   const int m_tiles = g.ntb * g.nth * g.ntw;
-  const int total_tiles = m_tiles / CG * n_blocks;  // work items (tile pairs when CG == 2)
+  const int nphase = g.nphase > 1 ? g.nphase : 1;
+  const int tiles_pp = m_tiles / CG * n_blocks;     // work items of one phase (tile pairs when CG == 2)
+  const int total_tiles = tiles_pp * nphase;
   const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
   const int kchunks = (g.Cin + 63) >> 6;   // a ragged last chunk is zero-filled by TMA (both operands)
   const int ksteps = g.ntaps / taps_per_stage * kchunks;   // pipeline steps per tile
@@ -108,14 +110,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int s = 0;
     uint32_t ph = 0;
     for (int tile = first_item; tile < total_tiles; tile += item_stride) {
-      const int n_blk = tile % n_blocks;
-      int m = (tile / n_blocks) * CG + cta_rank;
+      const int phase = tile / tiles_pp, tl = tile % tiles_pp;
+      const int n_blk = tl % n_blocks;
+      int m = (tl / n_blocks) * CG + cta_rank;
       const int tw = m % g.ntw;
       m /= g.ntw;
       const int th = m % g.nth;
       const int tb = m / g.nth;
       const int w0 = tw * g.TW * g.in_mul, h0 = th * g.TH * g.in_mul, b0 = tb * g.TB;
-      for (int t = 0; t < g.ntaps; t += taps_per_stage) {
+      for (int t = phase * g.ntaps; t < (phase + 1) * g.ntaps; t += taps_per_stage) {
         const int cw = w0 + g.dx[t], ch = h0 + g.dy[t];
         const int nsel = n_blk * block_n + cta_rank * (block_n / CG);
         for (int kc = 0; kc < kchunks; ++kc) {
@@ -204,8 +207,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t pacc = 0;
     bool store_pending = false;
     for (int tile = first_item; tile < total_tiles; tile += item_stride) {
-      const int n_blk = tile % n_blocks;
-      int m = (tile / n_blocks) * CG + cta_rank;
+      const int phase = tile / tiles_pp, tl = tile % tiles_pp;
+      const int o_ph = nphase > 1 ? phase >> 1 : g.o_ph, o_pw = nphase > 1 ? phase & 1 : g.o_pw;
+      const int n_blk = tl % n_blocks;
+      int m = (tl / n_blocks) * CG + cta_rank;
       const int tw = m % g.ntw;
       m /= g.ntw;
       const int th = m % g.nth;
@@ -215,7 +220,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool valid = gb < g.GB;
       const int rows_left = (g.GB - tb * g.TB) * g.TW * g.TH;     // rows of this tile that lie inside the batch
       const int nvalid = rows_left < 128 ? rows_left : 128;
-      const size_t pix = (static_cast<size_t>(gb) * g.OH + (gh * g.o_mul + g.o_ph)) * g.OW + (gw * g.o_mul + g.o_pw);
+      const size_t pix = (static_cast<size_t>(gb) * g.OH + (gh * g.o_mul + o_ph)) * g.OW + (gw * g.o_mul + o_pw);
       const size_t obase = pix * g.ldo + g.o_coff + n_blk * block_n;
 
       mbar_wait(&bars->tfull[acc], pacc);
@@ -464,7 +469,8 @@ bool tile_grid(int GB, int GH, int GW, int pixels, int* TB, int* TH, int* TW) {
 int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, int nslabs, ConvGeom g,
                       const float* bias, void* out, float* stats, cudaStream_t stream) {
   if (g.Cin % 8 != 0 || g.block_n % 32 != 0 || g.block_n > 256 || g.Cout % g.block_n != 0) return 2;
-  if (g.ntaps < 1 || g.ntaps > kMaxTaps) return 3;
+  if (g.nphase < 1) g.nphase = 1;
+  if (g.ntaps < 1 || g.ntaps * g.nphase > kMaxTaps) return 3;
   if (!tile_grid(g.GB, g.GH, g.GW, 128, &g.TB, &g.TH, &g.TW)) return 4;
   g.ntw = g.GW / g.TW;
   g.nth = g.GH / g.TH;
@@ -484,10 +490,10 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
     pair_mode = e ? atoi(e) : 1;
   }
   const int cg = (pair_mode && g.block_n == 256 && m_tiles % 2 == 0 && sms % 2 == 0 &&
-                  (long)m_tiles / 2 * (g.Cout / g.block_n) >= sms / 2) ? 2 : 1;
+                  (long)m_tiles / 2 * (g.Cout / g.block_n) * g.nphase >= sms / 2) ? 2 : 1;
   // A-tile reuse: taps sorted by (dy, dx) come in runs of 3 with equal dy and consecutive dx, one image row per tile
   {
-    for (int i = 1; i < g.ntaps; ++i)            // insertion sort of the tap list by (dy, dx)
+    for (int i = 1; i < g.ntaps && g.nphase == 1; ++i)   // insertion sort of the tap list by (dy, dx)
       for (int j = i; j > 0 && (g.dy[j] < g.dy[j - 1] || (g.dy[j] == g.dy[j - 1] && g.dx[j] < g.dx[j - 1])); --j) {
         int t;
         t = g.dy[j]; g.dy[j] = g.dy[j - 1]; g.dy[j - 1] = t;
@@ -499,7 +505,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
       const char* e = getenv("LUN_CONV_AREUSE");
       reuse_mode = e ? atoi(e) : 1;
     }
-    bool ok = reuse_mode && cg == 2 && g.ntaps % 3 == 0 && g.TW == 128 && g.TH == 1 && g.TB == 1 && g.in_mul == 1 &&
+    bool ok = reuse_mode && g.nphase == 1 && cg == 2 && g.ntaps % 3 == 0 && g.TW == 128 && g.TH == 1 && g.TB == 1 && g.in_mul == 1 &&
               g.block_n == 256;
     for (int i = 0; ok && i < g.ntaps; i += 3)
       ok = g.dy[i + 1] == g.dy[i] && g.dy[i + 2] == g.dy[i] && g.dx[i + 1] == g.dx[i] + 1 && g.dx[i + 2] == g.dx[i] + 2;
@@ -549,7 +555,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
       return 8;
     configured = true;
   }
-  const int total_items = m_tiles / cg * (g.Cout / g.block_n);
+  const int total_items = m_tiles / cg * (g.Cout / g.block_n) * g.nphase;
   int grid = sms;
   if (grid > total_items * cg) grid = total_items * cg;
   if (cg == 2) {

@@ -39,6 +39,9 @@ struct ConvGeom {
   int OH, OW, o_mul, o_ph, o_pw, ldo, o_coff;
   int flags;
   float slope;
+  // nphase > 1 (transposed conv, all output phases in ONE launch): the tap list holds nphase runs of ntaps taps; a work
+  // item is (phase, pixel tile, channel block) and phase p writes output phase (o_ph, o_pw) = (p >> 1, p & 1)
+  int nphase;
 };
 
 // Weight-gradient geometry: dW[slab[t]][co][ci] += sum over grid points of dY[b,h,w,co] * X[b, h*in_mul+dy, w*in_mul+dx, ci]

@@ -171,14 +171,14 @@ def convT4x4s2_fprop(x, w_packed, bias=None, out=None, img_stats=None):
     cout = w_packed.shape[1]
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, cout, device=x.device, dtype=torch.bfloat16)
-    if cout in (32, 64) and cin % 64 == 0 and H % 16 == 0 and W % 8 == 0 and _HALO_CONVT:
-        # thin stages: all four phases in one launch from a shared-memory halo tile (csrc/convt_halo_sm100.cu)
+    if _HALO_CONVT and out.is_contiguous() and w_packed.shape[0] == 16 and (H * W >= 128 or img_stats is None):
+        # one launch for all four phases: the fused-phase halo kernel for the thin stages (csrc/convt_halo_sm100.cu),
+        # the tap-list kernel with the phases batched as a work-item dimension otherwise
         _nhwc(x)
-        assert w_packed.shape[0] == 16 and w_packed.shape[2] == cin and out.is_contiguous()
+        assert w_packed.shape[2] == cin
         assert img_stats is None or img_stats.numel() == 2 * cout * B
-        check(_capi.lib().lun_convT4x4s2_halo_bf16(x.data_ptr(), B, H, W, cin, w_packed.data_ptr(), cout, _ptr(bias),
-                                                   out.data_ptr(), _ptr(img_stats), _stream()),
-              "lun_convT4x4s2_halo_bf16")
+        check(_capi.lib().lun_convT4x4s2_bf16(x.data_ptr(), B, H, W, cin, w_packed.data_ptr(), cout, _ptr(bias),
+                                              out.data_ptr(), _ptr(img_stats), _stream()), "lun_convT4x4s2_bf16")
         return out
     for ph in range(2):
         for pw in range(2):
