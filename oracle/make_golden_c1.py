@@ -4,10 +4,10 @@
 
 Run in the build container only (needs /root/reference; about five minutes on 8 host threads):
     python oracle/make_golden_c1.py
-Two real `TrainingManager._process_batch` calls (SURVEY.md App. C.1 harness) on 8 seeded sprites, dropout
+Three real `TrainingManager._process_batch` calls (SURVEY.md App. C.1 harness) on 8 seeded sprites, dropout
 probabilities set to 0 at run time (torch's Philox stream cannot be matched by a fused kernel; everything else -
-epsilon draw, reward baseline, clip, AdamW, cosine step - is the reference's). The fixture keeps the 12 metrics of both
-steps, the learning rates, the grad-None set, BatchNorm counters and a fingerprint (sum, |sum|, 8 samples) of every
+epsilon draw, reward baseline, clip, AdamW, cosine step - is the reference's). The fixture keeps the 12 metrics of all
+three steps, the learning rates, the grad-None set, BatchNorm counters and a fingerprint (sum, |sum|, 8 samples) of every
 gradient of step 0 and of every parameter after the optimizer step. Test infrastructure only.
 """
 import os
@@ -76,11 +76,17 @@ def main():
         m2 = tm._process_batch(x.clone(), 1)
         out["step1"] = {"metrics": m2, "vae_lr": tm.vae_optimizer.param_groups[0]["lr"],
                         "teacher_lr": tm.teacher_optimizer.param_groups[0]["lr"]}
+        m3 = tm._process_batch(x.clone(), 2)
+        out["step2"] = {"metrics": m3, "vae_lr": tm.vae_optimizer.param_groups[0]["lr"],
+                        "teacher_lr": tm.teacher_optimizer.param_groups[0]["lr"],
+                        "teacher_nbt": {k: int(v) for k, v in tm.teacher.state_dict().items()
+                                        if k.endswith("num_batches_tracked")}}
     path = os.path.join(ROOT, "tests", "golden", "golden_c1.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes; step 0 took %.1f s" % out["seconds_step0"])
     print(out["step0"]["metrics"])
     print(out["step1"]["metrics"])
+    print(out["step2"]["metrics"])
 
 
 if __name__ == "__main__":

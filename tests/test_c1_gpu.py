@@ -1,4 +1,4 @@
-"""BASELINE.json configs[0] ("C1": batch 8, latent 256 / emb 128 / feat 256) at FULL size: two trainer steps of
+"""BASELINE.json configs[0] ("C1": batch 8, latent 256 / emb 128 / feat 256) at FULL size: three trainer steps of
 lunaris_orion_b200.train_hybrid.TrainingManager on the B200 vs tests/golden/golden_c1.pt, which holds what the
 UNMODIFIED reference trainer produced for the same seeds and sprites on CPU fp32 (oracle/make_golden_c1.py).
 
@@ -102,3 +102,19 @@ def test_two_trainer_steps_at_c1_match_the_reference_trainer(cuda_dev, tmp_path)
     for k in ("quality_scores", "quality_reward"):
         assert abs(m1[k] - ref1["metrics"][k]) <= 0.08, (k, m1[k], ref1["metrics"][k])
     assert abs(tm.vae_optimizer.param_groups[0]["lr"] - ref1["vae_lr"]) < 1e-12
+    # third consecutive step (">= 3 consecutive steps"): two optimizer updates deep, the bf16 path and the
+    # fp32 reference have drifted apart a little more; BatchNorm counters and the schedule stay exact
+    if "step2" in gold:
+        m2 = tm._process_batch(x, 2)
+        ref2 = gold["step2"]
+        report["step2"] = {k: (m2[k], ref2["metrics"][k]) for k in ref2["metrics"]}
+        if os.path.isdir(out_dir):
+            json.dump(report, open(os.path.join(out_dir, "c1_parity_report.json"), "w"), indent=1, default=str)
+        for k in ("recon_loss", "vae_loss"):
+            assert abs(m2[k] - ref2["metrics"][k]) <= 0.05 * abs(ref2["metrics"][k]) + 1e-4, (k, m2[k], ref2["metrics"][k])
+        assert abs(m2["kl_loss"] - ref2["metrics"]["kl_loss"]) <= 0.10 * abs(ref2["metrics"]["kl_loss"]) + 1e-3
+        assert abs(m2["quality_scores"] - ref2["metrics"]["quality_scores"]) <= 0.10
+        assert abs(tm.vae_optimizer.param_groups[0]["lr"] - ref2["vae_lr"]) < 1e-12
+        sd = tm.teacher.state_dict()
+        for k, v in ref2["teacher_nbt"].items():
+            assert int(sd[k]) == v, k
