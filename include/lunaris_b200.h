@@ -237,6 +237,11 @@ int lun_flash_attn2d_dv_bf16(const void* qk, const void* dy, const float* lse, c
 int lun_flash_attn2d_dqk_bf16(const void* qk, const void* v, const void* dy, const float* lse, const float* dsum,
                               const float* gamma, void* dqk, int B, int N, int C, void* stream);
 
+/* bf16 kernel-operand shadow of an fp32 weight (rebuilt after every optimizer step): src [A][B][T] fp32 - a conv weight
+ * [Cout][Cin][kh*kw] or a ConvTranspose2d weight [Cin][Cout][kh*kw] - -> dst bf16 [T][A][B] (transpose = 0) or
+ * [T][B][A] (transpose = 1), the K-major slabs lun_conv_taps_bf16 / lun_convT4x4s2_bf16 read. */
+int lun_pack_weight_bf16(const float* src, void* dst, int A, int B, int T, int transpose, void* stream);
+
 /* Optimizer boundary (train_hybrid.py:906-922): clip_grad_norm_(max_norm) + AdamW over all tensors of one model in two
  * multi-tensor launches. table: device array of {float* param, grad, exp_avg, exp_avg_sq; long long numel} (40 bytes
  * each); chunks: device array of int2 {tensor index, chunk index} with 8192 elements per chunk; norm2: device float[1024]

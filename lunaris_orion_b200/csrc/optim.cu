@@ -74,6 +74,22 @@ __global__ void __launch_bounds__(256) multi_adamw_kernel(const OptTensor* __res
   }
 }
 
+// Kernel-operand shadow of an fp32 parameter after an optimizer step: src [A][B][T] fp32 (a conv weight [Cout][Cin][kh*kw]
+// or a transposed-conv weight [Cin][Cout][kh*kw]) -> dst bf16 [T][A][B] (transpose == 0) or [T][B][A] (transpose == 1),
+// the K-major slabs the implicit-GEMM kernels read. One launch per weight instead of torch's permute copy + cast.
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int A,
+                                                          int B, int T, int transpose) {
+  const long n = (long)A * B * T;
+  const int X = transpose ? B : A, Y = transpose ? A : B;       // dst is [T][X][Y]
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const int y = (int)(i % Y);
+    const int x = (int)((i / Y) % X);
+    const int t = (int)(i / ((long)X * Y));
+    const int a = transpose ? y : x, b = transpose ? x : y;
+    dst[i] = __float2bfloat16_rn(__ldg(src + ((long)a * B + b) * T + t));
+  }
+}
+
 }  // namespace lun
 
 using namespace lun;
@@ -98,6 +114,16 @@ int lun_multi_clip_adamw(const void* table, const void* chunks, int nchunks, con
   multi_adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const OptTensor*)table, (const int2*)chunks, nchunks,
                                                             norm2, npart, max_norm, lr, beta1, beta2, eps,
                                                             weight_decay, bias_c1, bias_c2_sqrt);
+  lun::note_launch(1);
+  return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
+}
+
+int lun_pack_weight_bf16(const float* src, void* dst, int A, int B, int T, int transpose, void* stream) {
+  if (A < 1 || B < 1 || T < 1) return LUN_E_SHAPE;
+  const long n = (long)A * B * T;
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  lun::pack_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (lun::bf16*)dst, A, B, T, transpose);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }

@@ -28,28 +28,39 @@ def _nhwc(t):
 
 
 # ------------------------------------------------------------------------------------------------ weight packing
+def _pack(w, transpose):
+    """fp32 [A,B,kh,kw] -> bf16 [kh*kw][A][B] (transpose False) or [kh*kw][B][A] (True): one kernel on the GPU
+    (csrc/optim.cu pack_weight_kernel), torch on the CPU (module construction / CPU-side tests only)."""
+    A, B, kh, kw = w.shape
+    w = w.detach()
+    if not w.is_cuda:
+        t = w.permute(2, 3, 1, 0) if transpose else w.permute(2, 3, 0, 1)
+        return t.reshape(kh * kw, B if transpose else A, A if transpose else B).to(torch.bfloat16).contiguous()
+    w = w.float().contiguous()
+    out = torch.empty(kh * kw, B if transpose else A, A if transpose else B, device=w.device, dtype=torch.bfloat16)
+    check(_capi.lib().lun_pack_weight_bf16(w.data_ptr(), out.data_ptr(), A, B, kh * kw, 1 if transpose else 0, _stream()),
+          "lun_pack_weight_bf16")
+    return out
+
+
 def pack_conv_weight(w):
     """[Cout,Cin,kh,kw] fp32 -> bf16 [kh*kw][Cout][Cin] (forward operand)."""
-    co, ci, kh, kw = w.shape
-    return w.detach().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16).contiguous()
+    return _pack(w, False)
 
 
 def pack_conv_weight_dgrad(w):
     """[Cout,Cin,kh,kw] -> bf16 [kh*kw][Cin][Cout] (data-gradient operand)."""
-    co, ci, kh, kw = w.shape
-    return w.detach().permute(2, 3, 1, 0).reshape(kh * kw, ci, co).to(torch.bfloat16).contiguous()
+    return _pack(w, True)
 
 
 def pack_convT_weight(w):
     """ConvTranspose2d weight [Cin,Cout,kh,kw] -> bf16 [kh*kw][Cout][Cin] (forward operand)."""
-    ci, co, kh, kw = w.shape
-    return w.detach().permute(2, 3, 1, 0).reshape(kh * kw, co, ci).to(torch.bfloat16).contiguous()
+    return _pack(w, True)
 
 
 def pack_convT_weight_dgrad(w):
     """ConvTranspose2d weight [Cin,Cout,kh,kw] -> bf16 [kh*kw][Cin][Cout] (data-gradient operand)."""
-    ci, co, kh, kw = w.shape
-    return w.detach().permute(2, 3, 0, 1).reshape(kh * kw, ci, co).to(torch.bfloat16).contiguous()
+    return _pack(w, False)
 
 
 # ------------------------------------------------------------------------------------------------ raw launchers

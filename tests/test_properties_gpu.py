@@ -123,3 +123,19 @@ def test_attention_fold_of_constant_chunks_returns_the_rows(cuda_dev):
     got = xbar[:, :nq].float().view(Bs, nq, 8, C)
     err = (got - want.unsqueeze(2)).abs().max().item()
     assert err <= 2e-2 * want.abs().max().item()
+
+
+@pytest.mark.gpu
+def test_weight_pack_kernel_matches_the_permutes_it_replaces(cuda_dev):
+    """lun_pack_weight_bf16 (one launch per weight after every optimizer step) reproduces, bit for bit, the four layout
+    conversions of ops.py: conv forward / data-gradient and transposed-conv forward / data-gradient operands."""
+    g = torch.Generator(device="cpu").manual_seed(9)
+    w = torch.randn(96, 40, 3, 3, generator=g).to(cuda_dev)
+    wt = torch.randn(40, 96, 4, 4, generator=g).to(cuda_dev)
+    bf = lambda t: t.to(torch.bfloat16).contiguous()
+    assert torch.equal(ops.pack_conv_weight(w), bf(w.permute(2, 3, 0, 1).reshape(9, 96, 40)))
+    assert torch.equal(ops.pack_conv_weight_dgrad(w), bf(w.permute(2, 3, 1, 0).reshape(9, 40, 96)))
+    assert torch.equal(ops.pack_convT_weight(wt), bf(wt.permute(2, 3, 1, 0).reshape(16, 96, 40)))
+    assert torch.equal(ops.pack_convT_weight_dgrad(wt), bf(wt.permute(2, 3, 0, 1).reshape(16, 40, 96)))
+    w1 = torch.randn(512, 128, 1, 1, generator=g).to(cuda_dev)
+    assert torch.equal(ops.pack_conv_weight(w1), bf(w1.view(1, 512, 128)))
