@@ -9,13 +9,15 @@ namespace lun {
 
 constexpr int kVT = 256;
 
-// mish(v) = v * tanh(softplus(v)). With e = exp(v): tanh(log(1+e)) = n / (n + 2), n = e^2 + 2e  (one exp, one divide;
-// for v > 20 tanh(softplus) == 1 in fp32, which is also torch's softplus threshold).
+// mish(v) = v * tanh(softplus(v)). With e = exp(v): tanh(log(1+e)) = n / (n + 2), n = e^2 + 2e  (one MUFU.EX2, one
+// MUFU.RCP). v is clamped at 20 (torch's softplus threshold): there e = 4.9e8, n = 2.4e17 and n / (n + 2) rounds to
+// exactly 1.0f, so no select is needed for the linear branch.
 __device__ __forceinline__ float mish_tanh_sp(float v, float* e_out) {
-  const float e = __expf(fminf(v, 20.f));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 20.f) * 1.4426950408889634f));
   *e_out = e;
   const float n = e * (e + 2.f);
-  return v > 20.f ? 1.f : __fdividef(n, n + 2.f);
+  return __fdividef(n, n + 2.f);
 }
 __device__ __forceinline__ float mish_f(float v) {
   float e;
@@ -32,7 +34,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float mish_grad_f(float v) {
   float e;
   const float t = mish_tanh_sp(v, &e);
-  const float sg = v > 20.f ? 1.f : __fdividef(e, 1.f + e);
+  const float sg = __fdividef(e, 1.f + e);      // == 1.0f for v >= 20 (e is clamped at exp(20))
   return t + v * (1.f - t * t) * sg;
 }
 
