@@ -169,3 +169,32 @@ def test_forward_after_an_optimizer_step_runs_on_the_updated_weights(cuda_dev, t
     assert (mu_live - mu_new).abs().max().item() < 0.02 * scale, "live modules ran on stale packed weights"
     assert moved > 0.2 * scale, "one AdamW step must move mu visibly (32768-wide fc), else this test proves nothing"
     assert (q_live - q_new).abs().max().item() < 0.05 * (q_new.abs().max().item() + 1.0)
+
+
+@pytest.mark.gpu
+def test_cli_trains_an_epoch_from_sprite_files_and_resumes(cuda_dev, tmp_path):
+    """The reference's command line end to end (train_hybrid.py:1076-1135 flags, generate.py:858-904 on-disk format):
+    sprites_000.npy + labels_000.csv -> one epoch through main() -> latest.pt / best.pt -> a second run with
+    --resume_from continues from the saved global step."""
+    import numpy as np
+    from lunaris_orion_b200 import train_hybrid as th
+    data = tmp_path / "data"
+    data.mkdir()
+    np.save(data / "sprites_000.npy", np.random.default_rng(1234).integers(0, 256, (12, 128, 128, 3), dtype=np.uint8))
+    with open(data / "labels_000.csv", "w") as f:
+        f.write("filename,category,prompt,seed,pixel_size,guidance_scale,pag_scale,num_steps\n")
+        for i in range(12):
+            f.write(f"s{i}.png,cat,prompt,{i},8,7.5,3.0,20\n")
+    out = tmp_path / "out"
+    argv = ["--data_dir", str(data), "--output_dir", str(out), "--batch_size", "4", "--num_epochs", "1",
+            "--gradient_accumulation_steps", "1", "--latent_dim", "64", "--embedding_dim", "32", "--feature_dim", "64"]
+    th.main(argv)
+    ck = torch.load(out / "checkpoints" / "latest.pt", weights_only=True)
+    assert ck["global_step"] == 3 and (out / "checkpoints" / "best.pt").exists()          # 12 sprites / batch 4
+    assert all(torch.isfinite(v).all() for v in ck["vae_state_dict"].values() if v.is_floating_point())
+    args = th.build_arg_parser().parse_args(argv + ["--resume_from", str(out / "checkpoints" / "latest.pt")])
+    tm = th.TrainingManager(args, device=cuda_dev)
+    assert tm.global_step == 3
+    assert abs(tm.vae_optimizer.param_groups[0]["lr"] - ck["vae_optimizer"]["param_groups"][0]["lr"]) < 1e-12
+    m = tm._process_batch(tc.images(4, 2).to(cuda_dev), 0)
+    assert all(v == v for v in m.values()) and tm.global_step == 4
