@@ -139,3 +139,42 @@ def test_weight_pack_kernel_matches_the_permutes_it_replaces(cuda_dev):
     assert torch.equal(ops.pack_convT_weight_dgrad(wt), bf(wt.permute(2, 3, 0, 1).reshape(16, 40, 96)))
     w1 = torch.randn(512, 128, 1, 1, generator=g).to(cuda_dev)
     assert torch.equal(ops.pack_conv_weight(w1), bf(w1.view(1, 512, 128)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,hw,tap", [(64, 64, (1, 2)), (64, 64, (3, 0)), (128, 32, (0, 0)), (128, 32, (2, 3))])
+def test_transposed_conv_delta_filter_is_an_exact_phase_shift(cuda_dev, cin, hw, tap):
+    """ConvTranspose2d(k4,s2,p1) with a filter that is the identity at ONE tap (kh, kw) and zero elsewhere scatters the
+    input to one output phase, BIT EXACTLY (single-term fp32 sums of exact bf16 products), zero elsewhere - at the thin
+    decoder shapes that run on the halo kernel (shifts read through UMMA descriptor offsets into the halo tile), and
+    identically through the four per-phase launches of the tap-list kernel."""
+    kh, kw = tap
+    cout = cin // 2
+    Bn = 3
+    g = torch.Generator(device="cpu").manual_seed(hw + kh * 4 + kw)
+    x = torch.randn(Bn, hw, hw, cin, generator=g).to(torch.bfloat16).to(cuda_dev)
+    w = torch.zeros(cin, cout, 4, 4, device=cuda_dev)
+    w[torch.arange(cout), torch.arange(cout), kh, kw] = 1.0          # output channel c copies input channel c
+    ref = torch.nn.functional.conv_transpose2d(x.float().permute(0, 3, 1, 2), w, stride=2, padding=1)
+    ref = ref.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    wp = ops.pack_convT_weight(w)
+    y = ops.convT4x4s2_fprop(x, wp)
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref)
+    saved = ops._HALO_CONVT
+    try:
+        ops._HALO_CONVT = False                                       # four launches of the generic kernel
+        y4 = ops.convT4x4s2_fprop(x, wp)
+    finally:
+        ops._HALO_CONVT = saved
+    assert torch.equal(y4, ref)
+    # random filter: the two implementations agree to one bf16 rounding of fp32 sums taken in different orders
+    wr = (torch.randn(cin, cout, 4, 4, generator=g) * 0.05).to(cuda_dev)
+    wpr = ops.pack_convT_weight(wr)
+    a = ops.convT4x4s2_fprop(x, wpr).float()
+    try:
+        ops._HALO_CONVT = False
+        b = ops.convT4x4s2_fprop(x, wpr).float()
+    finally:
+        ops._HALO_CONVT = saved
+    assert (a - b).abs().max().item() <= 2.0 ** -7 * b.abs().max().item()

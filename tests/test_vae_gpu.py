@@ -178,3 +178,49 @@ def test_generate_and_rank_keeps_only_images_above_the_threshold(cuda_dev):
     assert bool((sc >= thr - 0.2).all()) and bool((sc[:-1] >= sc[1:]).all())
     none, _ = scoring.generate_and_rank(vae, teacher, num_samples=2, quality_threshold=1.5, max_attempts=1, seed=3)
     assert none.shape[0] == 0
+
+
+@pytest.mark.gpu
+def test_self_attention2d_at_4096_tokens_matches_fp32_attention(cuda_dev):
+    """The flash kernels at a size where the N x N matrix is large (N = 4096, C = 256, 32 key tiles, both S buffers and
+    both P atoms cycling many times): forward and all gradients vs an fp32 evaluation of lunar_generate.py:66-78 on the
+    GPU (TF32 off). Tolerance 3 % of max |ref| per tensor."""
+    import torch
+    import torch.nn.functional as F
+    from lunaris_orion_b200 import lunar_generate as lg
+    torch.manual_seed(11)
+    C, HW, B = 256, 64, 1
+    att = lg.SelfAttention2d(C).to(cuda_dev)
+    with torch.no_grad():
+        att.gamma.fill_(0.8)
+        for m in (att.query_conv, att.key_conv):
+            m.weight.mul_(0.5)
+        for p in att.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    x = torch.randn(B, C, HW, HW, device=cuda_dev).to(torch.bfloat16).float()
+    dy = torch.randn(B, C, HW, HW, device=cuda_dev).to(torch.bfloat16).float()
+    xg = x.clone().requires_grad_(True)
+    y = att(xg)
+    y.backward(dy)
+    mine = {"x": xg.grad.clone(), **{k: p.grad.clone() for k, p in att.named_parameters()}}
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in att.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    N = HW * HW
+    q = F.conv2d(xr, w["query_conv.weight"], w["query_conv.bias"]).view(B, -1, N)
+    k = F.conv2d(xr, w["key_conv.weight"], w["key_conv.bias"]).view(B, -1, N)
+    v = F.conv2d(xr, w["value_conv.weight"], w["value_conv.bias"]).view(B, -1, N)
+    attn = torch.softmax(torch.bmm(q.permute(0, 2, 1), k), dim=-1)
+    out = torch.bmm(v, attn.permute(0, 2, 1)).view(B, C, HW, HW)
+    yr = w["gamma"] * out + xr
+    yr.backward(dy)
+    assert (y.detach() - yr.detach()).abs().max().item() < 2e-2 * yr.abs().max().item()
+    ref = {"x": xr.grad, **{k: t.grad for k, t in w.items()}}
+    errs = {}
+    for name, r in ref.items():
+        scale = r.abs().max().item()
+        if name == "key_conv.bias":
+            scale = ref["query_conv.bias"].abs().max().item()
+        if name == "gamma":
+            scale = max(scale, (dy * out.detach()).pow(2).sum().sqrt().item())
+        errs[name] = (mine[name] - r).abs().max().item() / (scale + 1e-12)
+    assert max(errs.values()) < 3e-2, errs
