@@ -28,6 +28,7 @@ extern "C" {
 #define LUN_EPI_LEAKY 2
 #define LUN_EPI_STATS 4
 #define LUN_EPI_OUT_F32 8
+#define LUN_EPI_DROP_SUM 256 /* internal: set by lun_conv_taps_dropsum_bf16 */
 #define LUN_EPI_STATS_IMG 64 /* with LUN_EPI_STATS: per-image sums, stats = fp32 [GB][2][Cout] (GroupNorm); the output
                               * grid of one image must hold at least 128 pixels */
 
@@ -48,6 +49,16 @@ int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const voi
                        int GB, int GH, int GW, int in_mul, int ntaps, const int* dy, const int* dx, const int* slab,
                        const float* bias, void* out, int OH, int OW, int o_mul, int o_ph, int o_pw, int ldo,
                        int o_coff, int flags, float slope, float* stats, void* stream);
+
+/* Same implicit GEMM, dense bf16 output, with the backward of an elementwise Dropout fused into the epilogue:
+ * colsum[0:Cout] += sum over output pixels of mask * bf16(out * 1/(1-p)), where mask is the counter-RNG dropout mask of
+ * lun_proj_expand_bf16 for (drop_seed, element index = pixel * ldo + channel). Used for the data-gradient of conv2
+ * (lunar_evaluator.py:249) whose result feeds proj_drop's backward and the proj bias gradient (:224-225): the
+ * separate pass over the 1 GB gradient tensor disappears. colsum: fp32 [2*Cout], first half written. */
+int lun_conv_taps_dropsum_bf16(const void* x, int XB, int XH, int XW, int Cin, const void* w_packed, int nslabs,
+                               int Cout, int GB, int GH, int GW, int in_mul, int ntaps, const int* dy, const int* dx,
+                               const int* slab, void* out, int OH, int OW, int ldo, float* colsum,
+                               unsigned long long drop_seed, float drop_p, void* stream);
 
 /* ConvTranspose2d(k=4, s=2, p=1) for thin stages (lunar_generate.py:181-187), all four output phases in one launch:
  * x [B,H,W,Cin] bf16 NHWC -> out [B,2H,2W,Cout] bf16 (+ bias). A CTA loads the 18x10 halo of a 16x8 input block once

@@ -56,6 +56,9 @@ SIGNATURES = {
                             c_void_p],
     "lun_convT4x4s2_halo_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p],
+    "lun_conv_taps_dropsum_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_int_p, c_int_p, c_int_p,
+                                   c_void_p, c_int, c_int, c_int, c_void_p, c_u64, c_float, c_void_p],
     "lun_wgrad_taps_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int_p, c_int_p, c_int_p, c_void_p, c_void_p],

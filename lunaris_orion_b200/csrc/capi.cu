@@ -3,6 +3,7 @@
 #include "conv_gemm.cuh"
 #include "launch_count.cuh"
 #include <atomic>
+#include <cuda_bf16.h>
 
 namespace lun {
 int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, int nslabs, ConvGeom g,
@@ -20,10 +21,11 @@ int lun_abi_version(void) { return 1; }
 int lun_num_sms(void) { return lun::num_sms(); }
 long long lun_launch_count(void) { return lun::g_launches.load(); }
 
-int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const void* w_packed, int nslabs, int Cout,
-                       int GB, int GH, int GW, int in_mul, int ntaps, const int* dy, const int* dx, const int* slab,
-                       const float* bias, void* out, int OH, int OW, int o_mul, int o_ph, int o_pw, int ldo,
-                       int o_coff, int flags, float slope, float* stats, void* stream) {
+static int conv_taps_impl(const void* x, int XB, int XH, int XW, int Cin, const void* w_packed, int nslabs, int Cout,
+                          int GB, int GH, int GW, int in_mul, int ntaps, const int* dy, const int* dx, const int* slab,
+                          const float* bias, void* out, int OH, int OW, int o_mul, int o_ph, int o_pw, int ldo,
+                          int o_coff, int flags, float slope, float* stats, unsigned long long drop_seed,
+                          float drop_p, void* stream) {
   if (ntaps < 1 || ntaps > lun::kMaxTaps) return LUN_E_TAPS;
   lun::ConvGeom g{};
   g.GB = GB; g.GH = GH; g.GW = GW;
@@ -34,8 +36,29 @@ int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const voi
   g.block_n = Cout >= 256 && Cout % 256 == 0 ? 256 : Cout >= 128 && Cout % 128 == 0 ? 128 : Cout % 64 == 0 ? 64 : 32;
   g.OH = OH; g.OW = OW; g.o_mul = o_mul; g.o_ph = o_ph; g.o_pw = o_pw; g.ldo = ldo; g.o_coff = o_coff;
   g.flags = flags; g.slope = slope;
+  g.drop_seed = drop_seed;
+  g.drop_thresh16 = drop_p > 0.f ? (unsigned int)(drop_p * 65536.f + 0.5f) : 0u;
+  g.drop_scale = drop_p > 0.f ? __bfloat162float(__float2bfloat16_rn(1.f / (1.f - drop_p))) : 1.f;
   return lun::launch_conv_fprop(x, XB, XH, XW, w_packed, nslabs, g, bias, out, stats,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int lun_conv_taps_bf16(const void* x, int XB, int XH, int XW, int Cin, const void* w_packed, int nslabs, int Cout,
+                       int GB, int GH, int GW, int in_mul, int ntaps, const int* dy, const int* dx, const int* slab,
+                       const float* bias, void* out, int OH, int OW, int o_mul, int o_ph, int o_pw, int ldo,
+                       int o_coff, int flags, float slope, float* stats, void* stream) {
+  return conv_taps_impl(x, XB, XH, XW, Cin, w_packed, nslabs, Cout, GB, GH, GW, in_mul, ntaps, dy, dx, slab, bias, out,
+                        OH, OW, o_mul, o_ph, o_pw, ldo, o_coff, flags & ~lun::EPI_DROP_SUM, slope, stats, 0ull, 0.f, stream);
+}
+
+int lun_conv_taps_dropsum_bf16(const void* x, int XB, int XH, int XW, int Cin, const void* w_packed, int nslabs,
+                               int Cout, int GB, int GH, int GW, int in_mul, int ntaps, const int* dy, const int* dx,
+                               const int* slab, void* out, int OH, int OW, int ldo, float* colsum,
+                               unsigned long long drop_seed, float drop_p, void* stream) {
+  // dense bf16 output through the TMA-store path; colsum[0:Cout] += sum over pixels of mask * bf16(out * 1/(1-p))
+  return conv_taps_impl(x, XB, XH, XW, Cin, w_packed, nslabs, Cout, GB, GH, GW, in_mul, ntaps, dy, dx, slab, nullptr, out,
+                        OH, OW, 1, 0, 0, ldo, 0, lun::EPI_STATS | lun::EPI_DROP_SUM, 1.f, colsum, drop_seed, drop_p,
+                        stream);
 }
 
 // defined in convt_halo_sm100.cu

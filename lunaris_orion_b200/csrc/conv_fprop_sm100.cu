@@ -14,6 +14,7 @@
 // Replaces the reference's F.conv2d / conv_transpose2d call sites (lunar_evaluator.py:242,249,133,134,255;
 // lunar_generate.py:36,41,95-116,169-187) and their autograd data-gradients.
 #include "conv_gemm.cuh"
+#include "elem_common.cuh"
 #include "ptx.cuh"
 #include "launch_count.cuh"
 #include <stdlib.h>
@@ -302,6 +303,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                          o3 = col + ((cj ^ 3u) << 4);
           const int left = nvalid - rg * 32;           // valid rows of this group (a ragged last batch tile)
           float a1 = 0.f, a2 = 0.f;
+          const bool drop_sum = g.flags & EPI_DROP_SUM;
+          // drop_key(seed, idx8) for idx8 < 2^30: seed_lo ^ (idx8 * 4) ^ seed_hi * 0x85EBCA6B
+          const uint32_t drop_k0 = static_cast<uint32_t>(g.drop_seed) ^ static_cast<uint32_t>(g.drop_seed >> 32) * 0x85EBCA6BU;
+          const uint32_t e_row0 =
+              static_cast<uint32_t>((static_cast<size_t>(tb) * g.OH + th) * g.OW + tw * 128 + rg * 32) *
+                  static_cast<uint32_t>(g.ldo) + static_cast<uint32_t>(g.o_coff + nb + lane);
 #pragma unroll 1
           for (int i0 = 0; i0 < 32; i0 += 8) {
             uint16_t hv[8];
@@ -313,7 +320,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const float f = i0 + u < left ? __uint_as_float(static_cast<uint32_t>(hv[u]) << 16) : 0.f;
+              float f = i0 + u < left ? __uint_as_float(static_cast<uint32_t>(hv[u]) << 16) : 0.f;
+              if (drop_sum) {
+                // replay of the elementwise dropout on the stored tensor: element index e = pixel * ldo + channel
+                // (32-bit, tile = 128 consecutive pixels - checked by the launcher); same stream as drop_keep1()
+                const uint32_t e = e_row0 + static_cast<uint32_t>(i0 + u) * static_cast<uint32_t>(g.ldo);
+                const uint32_t h = hash32((drop_k0 ^ ((e >> 3) << 2)) + ((e >> 1) & 3u));
+                const uint32_t k16 = (e & 1u) ? (h >> 16) : (h & 0xFFFFu);
+                f = k16 >= g.drop_thresh16 ? rbf(f * g.drop_scale) : 0.f;
+              }
               a1 += f;
               a2 = fmaf(f, f, a2);
             }
@@ -478,6 +493,10 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   if (g.TW * g.in_mul > 256 || g.TH * g.in_mul > 256 || g.TB > 256) return 5;
   if (g.Cout > 2048 && (g.flags & EPI_STATS)) return 6;
   if ((g.flags & EPI_STATS_IMG) && (!(g.flags & EPI_STATS) || g.TB != 1)) return 6;
+  if ((g.flags & EPI_DROP_SUM) &&
+      (!(g.flags & EPI_STATS) || (g.flags & (EPI_OUT_F32 | EPI_STATS_IMG)) || g.o_mul != 1 || g.TW != 128 || g.TH != 1 ||
+       g.TB != 1 || (double)g.GB * g.OH * g.OW * g.ldo >= 4294967296.0))
+    return 6;                                    // the fused replay indexes 128-pixel row tiles with 32-bit elements
   if (!(g.flags & EPI_OUT_F32) && (g.ldo % 8 || g.o_coff % 8)) return 7;
 
   CUtensorMap tmA, tmA2, tmB, tmO;
@@ -518,7 +537,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
       const char* e = getenv("LUN_CONV_COLSTATS");
       col_mode = e ? atoi(e) : 1;
     }
-    if (col_mode) g.flags |= EPI_COL_STATS;
+    if (col_mode || (g.flags & EPI_DROP_SUM)) g.flags |= EPI_COL_STATS;    // the masked sum only exists on this path
   }
   if (!(g.flags & EPI_OUT_F32) && g.o_mul == 1)
     g.flags |= EPI_TMA_STORE;

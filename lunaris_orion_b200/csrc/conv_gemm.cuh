@@ -15,6 +15,8 @@ enum : int {
   EPI_STATS = 4,      // per-channel sum / sum-of-squares of the stored (rounded) values -> stats[0:N], stats[N:2N]
   EPI_OUT_F32 = 8,    // store fp32 instead of bf16
   EPI_TMA_STORE = 32, // (set by the launcher) bf16 output leaves through a swizzled smem tile + TMA store
+  EPI_DROP_SUM = 256,  // with EPI_STATS on the TMA-store path: stats[0:N] += column sums of dropout_mask * bf16(y * scale)
+                       // (the mask is the counter RNG of the elementwise kernels, keyed by the output element index)
   EPI_COL_STATS = 128, // (set by the launcher) statistics are column sums read back from the staged output tile
   EPI_STATS_IMG = 64, // with EPI_STATS: statistics per IMAGE (GroupNorm): stats[b][0:N] sums, stats[b][N:2N] squares;
                       // needs one image per 128-pixel tile (TB == 1)
@@ -42,6 +44,10 @@ struct ConvGeom {
   // nphase > 1 (transposed conv, all output phases in ONE launch): the tap list holds nphase runs of ntaps taps; a work
   // item is (phase, pixel tile, channel block) and phase p writes output phase (o_ph, o_pw) = (p >> 1, p & 1)
   int nphase;
+  // EPI_DROP_SUM: the elementwise dropout this sum replays (seed, 16-bit drop threshold, bf16 1/(1-p))
+  unsigned long long drop_seed;
+  unsigned int drop_thresh16;
+  float drop_scale;
 };
 
 // Weight-gradient geometry: dW[slab[t]][co][ci] += sum over grid points of dY[b,h,w,co] * X[b, h*in_mul+dy, w*in_mul+dx, ci]

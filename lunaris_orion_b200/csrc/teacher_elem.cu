@@ -558,18 +558,21 @@ __global__ void __launch_bounds__(kEThreads) proj_bwd_gather_kernel(const bf16* 
   const bool active = lane_px < g.lanes;
   const int b = blockIdx.y, c0 = cgi * 8;
   float acc[1][8] = {};
+  // dbias == null: the column sums came out of the producing conv's epilogue (lun_conv_taps_dropsum_bf16); only the
+  // first nq rows of every image are visited (gather + mask)
+  const int lim = dbias ? HW : nq;
   if (active) {
-    for (int p0 = blockIdx.x * g.lanes * kU + lane_px; p0 < HW; p0 += gridDim.x * g.lanes * kU) {
+    for (int p0 = blockIdx.x * g.lanes * kU + lane_px; p0 < lim; p0 += gridDim.x * g.lanes * kU) {
       float vv[kU][8];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int p = p0 + u * g.lanes;
-        if (p < HW) load8(dh2 + ((size_t)b * HW + p) * C + c0, vv[u]);
+        if (p < lim) load8(dh2 + ((size_t)b * HW + p) * C + c0, vv[u]);
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int p = p0 + u * g.lanes;
-        if (p >= HW) continue;
+        if (p >= lim) continue;
         const size_t off = ((size_t)b * HW + p) * C + c0;
         float (&v)[8] = vv[u];
         if (thresh16) {
@@ -584,6 +587,7 @@ __global__ void __launch_bounds__(kEThreads) proj_bwd_gather_kernel(const bf16* 
       }
     }
   }
+  if (dbias == nullptr) return;
   float* const dst[1] = {dbias};
   block_channel_reduce<1>(acc, smem, C, lane_px, cgi, active, dst);
 }
@@ -741,7 +745,7 @@ int lun_proj_bwd_gather_bf16(const void* dh2, void* dpo_small, float* dbias, int
   const unsigned int th = drop_p > 0.f ? (unsigned int)(drop_p * 65536.f + 0.5f) : 0u;
   const float ds = drop_p > 0.f ? __bfloat162float(__float2bfloat16_rn(1.f / (1.f - drop_p))) : 1.f;
   const int lanes = kEThreads / (C / 8);
-  dim3 grid(elem_blocks_per_image(HW, C, B), B);
+  dim3 grid(elem_blocks_per_image(dbias ? HW : nq, C, B), B);
   proj_bwd_gather_kernel<<<grid, kEThreads, lanes * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)dh2, (bf16*)dpo_small, dbias, B, HW, C, nq, nq_pad, seed, th, ds);
   lun::note_launch(1);

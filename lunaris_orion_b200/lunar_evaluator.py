@@ -536,13 +536,22 @@ class _TeacherTrunk(torch.autograd.Function):
                 d_gamma, d_beta = ls * t2, ls * t1
                 dz4 = dz.view(B, H, W, C)
                 dw2 = ops.conv2d_wgrad(dz4, sv["h2"].view(B, H, W, C), 3, 1, 1)
-                dh2 = ops.conv2d_dgrad(dz4, _packed(blk.conv2[0].weight, "dgrad"), 3, 1, 1, (H, W))
-                del dz, dz4
                 a = sv["att"]
-                dpo = torch.zeros(B, a["nq_pad"], C, device=dh2.device, dtype=torch.bfloat16)
-                dbp = torch.zeros(C, device=dh2.device)
-                check(_capi.lib().lun_proj_bwd_gather_bf16(dh2.data_ptr(), dpo.data_ptr(), dbp.data_ptr(), B, HW, C,
-                                                           a["nq"], a["nq_pad"], a["seed"], float(a["p_proj"]),
+                # conv2's data gradient with proj_drop's backward folded into its epilogue: the proj bias gradient
+                # (column sums of mask * dh2 / (1-p)) comes out of the conv, only the nq surviving rows are re-read
+                dpo = torch.zeros(B, a["nq_pad"], C, device=dz.device, dtype=torch.bfloat16)
+                if ops.drop_sum_ok(B, H, W, C):
+                    colsum = torch.zeros(2 * C, device=dz.device)
+                    dh2 = ops.conv2d_dgrad(dz4, _packed(blk.conv2[0].weight, "dgrad"), 3, 1, 1, (H, W),
+                                           drop_sum=(a["seed"], a["p_proj"], colsum))
+                    dbp = colsum[:C]
+                else:                                # small feature maps: a separate pass sums the masked gradient
+                    dh2 = ops.conv2d_dgrad(dz4, _packed(blk.conv2[0].weight, "dgrad"), 3, 1, 1, (H, W))
+                    dbp = torch.zeros(C, device=dz.device)
+                del dz, dz4
+                check(_capi.lib().lun_proj_bwd_gather_bf16(dh2.data_ptr(), dpo.data_ptr(),
+                                                           None if ops.drop_sum_ok(B, H, W, C) else dbp.data_ptr(), B,
+                                                           HW, C, a["nq"], a["nq_pad"], a["seed"], float(a["p_proj"]),
                                                            _stream()), "lun_proj_bwd_gather_bf16")
                 del dh2
                 dwp = ops.linear_wgrad(dpo.view(B * a["nq_pad"], C), a["att_small"].view(B * a["nq_pad"], C))

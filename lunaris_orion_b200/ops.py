@@ -133,8 +133,16 @@ def conv2d_fprop(x, w_packed, k, stride, pad, bias=None, act_leaky=False, stats=
                      flags=flags, slope=slope, stats=stats, img_stats=img_stats)
 
 
-def conv2d_dgrad(dy, w_packed_dgrad, k, stride, pad, in_hw, out=None):
-    """Gradient of F.conv2d w.r.t. its input. dy: [B,OH,OW,Cout] bf16; returns [B,H,W,Cin] bf16."""
+def drop_sum_ok(B, H, W, C):
+    """The fused dropout-backward column sum of conv2d_dgrad works on 128-pixel row tiles with 32-bit element indices."""
+    return W % 128 == 0 and B * H * W * C < 2 ** 32
+
+
+def conv2d_dgrad(dy, w_packed_dgrad, k, stride, pad, in_hw, out=None, drop_sum=None):
+    """Gradient of F.conv2d w.r.t. its input. dy: [B,OH,OW,Cout] bf16; returns [B,H,W,Cin] bf16.
+    drop_sum = (seed, p, colsum fp32 [2*Cin]): the epilogue also accumulates colsum[:Cin] += sum over pixels of
+    dropout_mask(seed) * bf16(dx / (1-p)) - the backward of an elementwise Dropout that consumed dx's forward twin
+    (proj_drop, lunar_evaluator.py:225) - so no separate pass reads dx for the bias gradient."""
     B, OH, OW, _ = dy.shape
     H, W = in_hw
     cin = w_packed_dgrad.shape[1]
@@ -142,6 +150,16 @@ def conv2d_dgrad(dy, w_packed_dgrad, k, stride, pad, in_hw, out=None):
         out = torch.empty(B, H, W, cin, device=dy.device, dtype=torch.bfloat16)
     if stride == 1:
         taps = [(pad - kh, pad - kw, kh * k + kw) for kh in range(k) for kw in range(k)]
+        if drop_sum is not None:
+            seed, p, colsum = drop_sum
+            _nhwc(dy)
+            assert colsum.dtype == torch.float32 and colsum.numel() == 2 * cin and out.is_contiguous()
+            check(_capi.lib().lun_conv_taps_dropsum_bf16(
+                dy.data_ptr(), B, OH, OW, dy.shape[-1], w_packed_dgrad.data_ptr(), w_packed_dgrad.shape[0], cin,
+                B, H, W, 1, len(taps), int_array([t[0] for t in taps]), int_array([t[1] for t in taps]),
+                int_array([t[2] for t in taps]), out.data_ptr(), H, W, cin, colsum.data_ptr(), seed, float(p),
+                _stream()), "lun_conv_taps_dropsum_bf16")
+            return out
         return conv_taps(dy, w_packed_dgrad, cin, (B, H, W), 1, taps, out, (H, W))
     assert stride == 2 and H % 2 == 0 and W % 2 == 0
     # input pixel ih = 2*j + ph receives dy[oh] * w[kh] with ih = 2*oh - pad + kh  ->  oh = j + (ph + pad - kh) / 2

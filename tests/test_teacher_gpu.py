@@ -148,3 +148,43 @@ def test_teacher_trunk_feat256_config2_shapes(cuda_dev):
     assert rep["grad_keys_equal"]
     assert rep["pool"] <= 3 * rep["cal_pool"] + 2e-3
     assert rep["grad_rel_max"] <= 3 * rep["cal_grad_rel_max"] + 0.02, rep["grad_worst"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,hw,p", [(64, 128, 0.1), (512, 128, 0.1), (128, 128, 0.0)])
+def test_conv_epilogue_replays_dropout_for_the_bias_gradient(cuda_dev, C, hw, p):
+    """lun_conv_taps_dropsum_bf16: the 3x3 data-gradient conv whose epilogue also sums mask * bf16(dx / (1-p)) per
+    channel (proj_drop backward + proj bias gradient, lunar_evaluator.py:224-225) equals the two-step path it replaces
+    (plain conv, then lun_proj_bwd_gather_bf16 over the whole tensor): same dx bit for bit, same column sums to fp32
+    summation order, same mask as the forward lun_proj_expand_bf16 (seeded counter RNG)."""
+    import ctypes
+    from lunaris_orion_b200 import _capi, ops
+    lib = _capi.lib()
+    B, seed = 2, 987654321
+    nq = hw * hw // 32 + 31
+    nq_pad = (nq + 7) // 8 * 8
+    g = torch.Generator().manual_seed(C + hw)
+    dz = torch.randn(B, hw, hw, C, generator=g).to(torch.bfloat16).to(cuda_dev)
+    w = (torch.randn(C, C, 3, 3, generator=g) * 0.05).to(cuda_dev)
+    wd = ops.pack_conv_weight_dgrad(w)
+    colsum = torch.zeros(2 * C, device=cuda_dev)
+    assert ops.drop_sum_ok(B, hw, hw, C) and not ops.drop_sum_ok(B, 32, 32, C)
+    with pytest.raises(_capi.LunarisB200Error):          # narrower rows are refused, never silently mis-indexed
+        ops.conv2d_dgrad(dz[:, :32, :32].contiguous(), wd, 3, 1, 1, (32, 32), drop_sum=(seed, p, colsum))
+    dx_fused = ops.conv2d_dgrad(dz, wd, 3, 1, 1, (hw, hw), drop_sum=(seed, p, colsum))
+    dx_plain = ops.conv2d_dgrad(dz, wd, 3, 1, 1, (hw, hw))
+    assert torch.equal(dx_fused, dx_plain)
+    dpo = torch.zeros(B, nq_pad, C, device=cuda_dev, dtype=torch.bfloat16)
+    db = torch.zeros(C, device=cuda_dev)
+    s = torch.cuda.current_stream().cuda_stream
+    _capi.check(lib.lun_proj_bwd_gather_bf16(dx_plain.data_ptr(), dpo.data_ptr(), db.data_ptr(), B, hw * hw, C, nq,
+                                             nq_pad, seed, ctypes.c_float(p), s), "gather")
+    dpo2 = torch.zeros_like(dpo)
+    _capi.check(lib.lun_proj_bwd_gather_bf16(dx_plain.data_ptr(), dpo2.data_ptr(), None, B, hw * hw, C, nq, nq_pad, seed,
+                                             ctypes.c_float(p), s), "gather rows only")
+    torch.cuda.synchronize()
+    assert torch.equal(dpo, dpo2)
+    scale = db.abs().max().item() + 1e-6
+    assert (colsum[:C] - db).abs().max().item() < 2e-3 * scale, ((colsum[:C] - db).abs().max().item(), scale)
+    if p == 0.0:
+        assert (colsum[:C] - dx_plain.float().sum((0, 1, 2))).abs().max().item() < 2e-3 * scale
