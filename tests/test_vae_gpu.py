@@ -224,3 +224,41 @@ def test_self_attention2d_at_4096_tokens_matches_fp32_attention(cuda_dev):
             scale = max(scale, (dy * out.detach()).pow(2).sum().sqrt().item())
         errs[name] = (mine[name] - r).abs().max().item() / (scale + 1e-12)
     assert max(errs.values()) < 3e-2, errs
+
+
+@pytest.mark.gpu
+def test_fused_decoder_tail_equals_the_two_kernels_it_replaces(cuda_dev):
+    """lun_gn_mish_final_conv_tanh_fwd (GroupNorm + Mish applied while a halo tile is staged, 32->3 conv on mma.sync,
+    tanh) vs lun_gn_mish_fwd_bf16 followed by lun_final_conv_tanh_fwd on the normalised tensor: the saved activation h
+    is bit-identical, the images agree to the SFU tanh's 2^-11."""
+    import ctypes
+    import torch
+    from lunaris_orion_b200 import _capi
+    lib = _capi.lib()
+    B, H = 3, 128
+    g = torch.Generator().manual_seed(4)
+    t = (torch.randn(B, H * H, 32, generator=g) * 1.5).to(torch.bfloat16).to(cuda_dev)
+    gamma = (torch.rand(32, generator=g) + 0.5).to(cuda_dev)
+    beta = (torch.randn(32, generator=g) * 0.1).to(cuda_dev)
+    w = (torch.randn(3, 32, 3, 3, generator=g) * 0.1).to(cuda_dev)
+    bias = (torch.randn(3, generator=g) * 0.1).to(cuda_dev)
+    st = torch.zeros(B, 2, 32, device=cuda_dev)
+    s = torch.cuda.current_stream().cuda_stream
+    P = lambda x: ctypes.c_void_p(x.data_ptr())
+    _capi.check(lib.lun_image_channel_stats_bf16(P(t), P(st), B, H * H, 32, s), "stats")
+    h_fused = torch.empty_like(t)
+    r_fused = torch.empty(B, 3, H, H, device=cuda_dev)
+    _capi.check(lib.lun_gn_mish_final_conv_tanh_fwd(P(t), P(st), P(gamma), P(beta), P(w), P(bias), P(h_fused), P(r_fused),
+                                                    B, H, H, 8, ctypes.c_float(1e-5), s), "fused tail")
+    h_two = torch.empty_like(t)
+    r_two = torch.empty_like(r_fused)
+    _capi.check(lib.lun_gn_mish_fwd_bf16(P(t), P(st), P(gamma), P(beta), None, None, P(h_two), B, H * H, 32, 8,
+                                         ctypes.c_float(1e-5), s), "gn_mish")
+    _capi.check(lib.lun_final_conv_tanh_fwd(P(h_two), P(w), P(bias), P(r_two), B, H, H, s), "final conv")
+    torch.cuda.synchronize()
+    assert torch.equal(h_fused, h_two)
+    assert (r_fused - r_two).abs().max().item() < 2e-3
+    # and against fp32 torch on the same bf16-rounded activation
+    ref = torch.tanh(torch.nn.functional.conv2d(h_two.float().view(B, H, H, 32).permute(0, 3, 1, 2),
+                                                w.to(torch.bfloat16).float(), bias, padding=1))
+    assert (r_fused - ref).abs().max().item() < 1e-2
