@@ -233,6 +233,20 @@ def decoder_forward(z, skips, sd, p="decoder"):
     return torch.tanh(_conv(h, sd, p + ".final_conv", padding=1))
 
 
+def self_attention2d(x, sd, p=""):
+    """SelfAttention2d.forward (lunar_generate.py:66-78): q, k = 1x1 convs to C/8, v = 1x1 conv to C; attention =
+    softmax_j(q_i . k_j) over all N = H*W positions (no scaling); out = v attention^T; gamma * out + x.
+    sd keys: query_conv / key_conv / value_conv .weight/.bias, gamma."""
+    B, C, H, W = x.shape
+    N = H * W
+    q = F.conv2d(x, sd[p + "query_conv.weight"], sd[p + "query_conv.bias"]).view(B, -1, N)
+    k = F.conv2d(x, sd[p + "key_conv.weight"], sd[p + "key_conv.bias"]).view(B, -1, N)
+    v = F.conv2d(x, sd[p + "value_conv.weight"], sd[p + "value_conv.bias"]).view(B, -1, N)
+    attn = torch.softmax(torch.bmm(q.permute(0, 2, 1), k), dim=-1)
+    out = torch.bmm(v, attn.permute(0, 2, 1)).view(B, C, H, W)
+    return sd[p + "gamma"] * out + x, out
+
+
 def vae_forward(x, sd, eps):
     """LunarisCoreVAE.forward with the reparameterisation noise supplied (lunar_generate.py:259-276)."""
     mu, logvar, skips = encoder_forward(x, sd)

@@ -107,3 +107,25 @@ def test_vae_matches_reference(ref):
     z = torch.randn(3, LAT)
     with torch.no_grad():
         assert torch.allclose(R.decoder_forward(z, [], sd), vae.decoder(z, []), atol=1e-5)
+
+
+def test_self_attention2d_restatement_matches_reference_class(ref):
+    """oracle.restatement.self_attention2d (the formula the GPU parity tests of the flash kernels compare against) ==
+    the reference's own SelfAttention2d module (lunar_generate.py:56-78), outputs and all gradients, fp32 CPU."""
+    lg, _ = ref
+    torch.manual_seed(5)
+    att = lg.SelfAttention2d(32)
+    with torch.no_grad():
+        att.gamma.fill_(0.7)
+    sd = _sd_leaf(att)
+    x = torch.randn(2, 32, 16, 16)
+    xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y_ref = att(xr)
+    y, _ = R.self_attention2d(xo, sd)
+    assert torch.allclose(y, y_ref, atol=1e-5)
+    g = torch.randn_like(y)
+    y_ref.backward(g)
+    y.backward(g)
+    assert torch.allclose(xo.grad, xr.grad, atol=1e-5)
+    for n, p in att.named_parameters():
+        assert torch.allclose(sd[n].grad, p.grad, atol=1e-6 + 1e-4 * p.grad.abs().max().item()), n

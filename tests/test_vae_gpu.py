@@ -104,15 +104,10 @@ def test_self_attention2d_backward_matches_autograd_of_reference_math(cuda_dev, 
     mine = {"x": xg.grad.cpu()}
     mine.update({k: p.grad.cpu() for k, p in att.named_parameters()})
 
+    from oracle import restatement as R
     w = {k: v.detach().cpu().float().requires_grad_(True) for k, v in att.state_dict().items()}
     xr = x.clone().requires_grad_(True)
-    N = HW * HW
-    q = F.conv2d(xr, w["query_conv.weight"], w["query_conv.bias"]).view(B, -1, N)
-    k = F.conv2d(xr, w["key_conv.weight"], w["key_conv.bias"]).view(B, -1, N)
-    v = F.conv2d(xr, w["value_conv.weight"], w["value_conv.bias"]).view(B, -1, N)
-    attn = torch.softmax(torch.bmm(q.permute(0, 2, 1), k), dim=-1)
-    out = torch.bmm(v, attn.permute(0, 2, 1)).view(B, C, HW, HW)
-    yr = w["gamma"] * out + xr
+    yr, out = R.self_attention2d(xr, w)              # pinned against the reference class in test_oracle_vs_reference.py
     assert (y.detach().cpu() - yr.detach()).abs().max().item() / yr.abs().max().item() < 2e-2
     yr.backward(dy)
     ref = {"x": xr.grad}
@@ -203,15 +198,10 @@ def test_self_attention2d_at_4096_tokens_matches_fp32_attention(cuda_dev):
     y = att(xg)
     y.backward(dy)
     mine = {"x": xg.grad.clone(), **{k: p.grad.clone() for k, p in att.named_parameters()}}
+    from oracle import restatement as R
     w = {k: v.detach().clone().requires_grad_(True) for k, v in att.state_dict().items()}
     xr = x.clone().requires_grad_(True)
-    N = HW * HW
-    q = F.conv2d(xr, w["query_conv.weight"], w["query_conv.bias"]).view(B, -1, N)
-    k = F.conv2d(xr, w["key_conv.weight"], w["key_conv.bias"]).view(B, -1, N)
-    v = F.conv2d(xr, w["value_conv.weight"], w["value_conv.bias"]).view(B, -1, N)
-    attn = torch.softmax(torch.bmm(q.permute(0, 2, 1), k), dim=-1)
-    out = torch.bmm(v, attn.permute(0, 2, 1)).view(B, C, HW, HW)
-    yr = w["gamma"] * out + xr
+    yr, out = R.self_attention2d(xr, w)              # fp32 on the GPU (TF32 off, tests/conftest.py)
     yr.backward(dy)
     assert (y.detach() - yr.detach()).abs().max().item() < 2e-2 * yr.abs().max().item()
     ref = {"x": xr.grad, **{k: t.grad for k, t in w.items()}}
