@@ -23,6 +23,7 @@
 #include "conv_gemm.cuh"
 #include "launch_count.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace lun {
 
@@ -46,19 +47,27 @@ struct __align__(16) FaBars {
 };
 
 // qk: [B*N, 128] bf16 rows = [q (64, zero padded) | k (64, zero padded)];  v: [B, N, C] bf16;  x, y: [B, N, C] bf16
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns 256 queries. Each CTA keeps its own 128 query rows, P tile
+// and accumulators, but loads only HALF of every streamed tile (64 of the 128 keys of K, half of V's channels): the
+// kernel is L2->SM bound with one CTA per 128 queries (7.8 TB/s), and pairing halves the operand bytes per FLOP.
+// tmK: the qk matrix with 128/CG-row boxes (the streamed K / Q tiles).
+template <int CG>
 __global__ void __launch_bounds__(kFaThreads, 1)
-flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV,
                     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma, int N, int C,
                     int vw, const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ o_out,
                     float* __restrict__ lse_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int vatoms = vw / 64;                       // 64-channel atoms of the value slice
+  const int vatoms = vw / 64 / CG;                  // 64-channel atoms of the value slice held by THIS CTA
+  constexpr int kKBytes = kFaTileBytes / CG;        // this CTA's share of a streamed K tile: 128/CG keys
   uint8_t* sQ = smem;                               // [128][64]
-  uint8_t* sK = sQ + kFaTileBytes;                  // 2 x [128][64]
-  uint8_t* sP = sK + 2 * kFaTileBytes;              // 2 atoms x [128 rows][64 keys]  (K-major A operand)
+  uint8_t* sK = sQ + kFaTileBytes;                  // 2 x [128/CG][64]
+  uint8_t* sP = sK + 2 * kKBytes;                   // 2 atoms x [128 rows][64 keys]  (K-major A operand)
   uint8_t* sV = sP + 2 * kFaTileBytes;              // 2 x vatoms x [128 keys][64 ch] (N-major B operand)
   FaBars* bars = reinterpret_cast<FaBars*>(sV + 2 * vatoms * kFaTileBytes);
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, b = blockIdx.y, vs = blockIdx.z;
@@ -71,6 +80,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQK);
+    prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     mbar_init(&bars->q_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -79,19 +89,25 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->v_empty[i], 1);
       mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->s_empty[i], 16);
-      mbar_init(&bars->p_full[i], 8);
+      mbar_init(&bars->s_empty[i], 16 * CG);       // softmax warps of both CTAs report to the leader
+      mbar_init(&bars->p_full[i], 8 * CG);
       mbar_init(&bars->p_empty[i], 1);
     }
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, tmem_cols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(&bars->tmem_base, tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&bars->tmem_base, tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();                  // peer barriers initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   const uint32_t tmem_s = tmem_base;                // 2 x 128 columns: S double buffer
@@ -101,28 +117,42 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const long row0 = (long)b * N;
-      mbar_expect_tx(&bars->q_full, kFaTileBytes);
-      tma_load_2d(sQ, &tmQK, &bars->q_full, own_col, (int)(row0 + qt * 128));
+      // pair mode: the full barriers live in the leader CTA; it announces the bytes of both CTAs
+      if (cta_rank == 0) mbar_expect_tx(&bars->q_full, CG * kFaTileBytes);
+      if (CG == 2) tma_load_2d_pair(sQ, &tmQK, &bars->q_full, own_col, (int)(row0 + qt * 128));
+      else tma_load_2d(sQ, &tmQK, &bars->q_full, own_col, (int)(row0 + qt * 128));
       for (int t = 0; t < steps; ++t) {
         const int j = t < first_b ? t : t - first_b;
         const int ks = t & 1;
         mbar_wait(&bars->k_empty[ks], ((t >> 1) & 1) ^ 1);
-        mbar_expect_tx(&bars->k_full[ks], kFaTileBytes);
-        tma_load_2d(sK + ks * kFaTileBytes, &tmQK, &bars->k_full[ks], other_col, (int)(row0 + j * 128));
+        if (cta_rank == 0) mbar_expect_tx(&bars->k_full[ks], kFaTileBytes);
+        const int krow = (int)(row0 + j * 128 + cta_rank * (128 / CG));           // this CTA's 128/CG keys
+        if (CG == 2) tma_load_2d_pair(sK + ks * kKBytes, &tmK, &bars->k_full[ks], other_col, krow);
+        else tma_load_2d(sK + ks * kKBytes, &tmK, &bars->k_full[ks], other_col, krow);
         if (t >= first_b) {
           const int vsx = j & 1;
           mbar_wait(&bars->v_empty[vsx], ((j >> 1) & 1) ^ 1);
-          mbar_expect_tx(&bars->v_full[vsx], vatoms * kFaTileBytes);
-          for (int a = 0; a < vatoms; ++a)
-            tma_load_4d(sV + (vsx * vatoms + a) * kFaTileBytes, &tmV, &bars->v_full[vsx], vs * vw + a * 64, j * 128, 0,
-                        b);
+          if (cta_rank == 0) mbar_expect_tx(&bars->v_full[vsx], CG * vatoms * kFaTileBytes);
+          for (int a = 0; a < vatoms; ++a) {
+            const int ch = vs * vw + (cta_rank * vatoms + a) * 64;                // this CTA's channels of the slice
+            if (CG == 2) tma_load_4d_pair(sV + (vsx * vatoms + a) * kFaTileBytes, &tmV, &bars->v_full[vsx], ch, j * 128, 0, b);
+            else tma_load_4d(sV + (vsx * vatoms + a) * kFaTileBytes, &tmV, &bars->v_full[vsx], ch, j * 128, 0, b);
+          }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);   // S = Q K^T      (both K-major)
-    const uint32_t idesc_o = make_idesc_bf16(128, vw, false, true);     // O += P V       (A K-major, B N-major)
+  } else if (warp == 1 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (the leader CTA of a pair)
+    const uint32_t idesc_s = make_idesc_bf16(128 * CG, 128, false, false);   // S = Q K^T      (both K-major)
+    const uint32_t idesc_o = make_idesc_bf16(128 * CG, vw, false, true);     // O += P V       (A K-major, B N-major)
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accumulate) {
+      if (CG == 2) umma_bf16_pair(d, ad, bd, idesc, accumulate);
+      else umma_bf16(d, ad, bd, idesc, accumulate);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (CG == 2) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     mbar_wait(&bars->q_full, 0);
     auto issue_s = [&](int t) {                      // S_t into TMEM buffer t & 1
       const int ks = t & 1;
@@ -131,11 +161,11 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       tc_fence_after();
       if (elect_one()) {
         const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + ks * kFaTileBytes), 0, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + ks * kKBytes), 0, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s + ks * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&bars->k_empty[ks]);
-        umma_commit(&bars->s_full[ks]);
+        for (int k = 0; k < 4; ++k) mma(tmem_s + ks * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        commit(&bars->k_empty[ks]);
+        commit(&bars->s_full[ks]);
       }
       __syncwarp();
     };
@@ -158,12 +188,12 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
               const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + a * kFaTileBytes) + (k & 3) * 32, 0, 1024);
               const uint64_t bdesc =
                   make_smem_desc_sw128(smem_u32(sV + vsx * vatoms * kFaTileBytes) + k * 2048, kFaTileBytes, 1024);
-              umma_bf16(tmem_o, adesc, bdesc, idesc_o, (j | k) != 0);
+              mma(tmem_o, adesc, bdesc, idesc_o, (j | k) != 0);
             }
-            umma_commit(&bars->p_empty[a]);
+            commit(&bars->p_empty[a]);
             if (a == 1) {
-              umma_commit(&bars->v_empty[vsx]);
-              if (j == ntiles - 1) umma_commit(&bars->o_full);
+              commit(&bars->v_empty[vsx]);
+              if (j == ntiles - 1) commit(&bars->o_full);
             }
           }
           __syncwarp();
@@ -171,8 +201,12 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ------------------------------------------------------------ softmax + epilogue (warps 2..17)
+    auto arrive = [&](uint64_t* bar) {              // barriers the MMA issuer waits on live in the leader CTA
+      if (CG == 2) mbar_arrive_cluster(bar, 0);
+      else mbar_arrive(bar);
+    };
     const int q = warp & 3;                         // TMEM lane quarter
     const int cq = (warp - 2) >> 2;                 // column quarter (32 of the 128 scores of a row) of the S tile
     const int hf = cq >> 1;                         // P atom (64 keys) this warp writes into
@@ -189,7 +223,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
+      if (lane == 0) arrive(&bars->s_empty[sb]);
 #pragma unroll
       for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
     }
@@ -209,7 +243,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
+      if (lane == 0) arrive(&bars->s_empty[sb]);
       // this thread's 32 keys = half of atom hf of the P tile: 4 chunks of 16 bytes, chunk index swizzled by row & 7
       const float4* lse_t = reinterpret_cast<const float4*>(lse_in + (size_t)b * N + j * 128 + cq * 32);   // dv_mode only
       // exp(s - m) = exp2(s * log2e - m * log2e): one FFMA + one MUFU.EX2 per score
@@ -246,7 +280,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p_full[hf]);
+      if (lane == 0) arrive(&bars->p_full[hf]);
     }
     // epilogue: O / rowsum, y = gamma * O + x  (backward: dV = gamma * O); training forward also keeps O and logsumexp
     float inv_l = 1.f;
@@ -290,10 +324,12 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -306,23 +342,54 @@ static int launch_flash(const void* qk, const void* v, const void* x, void* y, c
   if (N % 128 || C % 64 || C > 512) return LUN_E_SHAPE;
   const int vw = C > 256 ? 256 : C;
   if (C % vw) return LUN_E_SHAPE;
-  CUtensorMap tmQK, tmV;
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char* e = getenv("LUN_FLASH_PAIR");
+    pair_mode = e ? atoi(e) : 1;
+  }
+  // CTA pairs: 256 queries per cluster, every streamed K / V tile split between the two CTAs
+  const int cg = (pair_mode && (N / 128) % 2 == 0 && vw % 128 == 0) ? 2 : 1;
+  CUtensorMap tmQK, tmK, tmV;
   int rc = make_tmap_2d(&tmQK, qk, (long)B * N, 128, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmK, qk, (long)B * N, 128, 128 / cg);
   if (rc) return rc;
   rc = make_tmap_nhwc(&tmV, v, B, 1, N, C, 128, 1, 1, 1);     // {C, W=N, H=1, B}: boxes of 64 ch x 128 keys
   if (rc) return rc;
-  const int vatoms = vw / 64;
-  const int smem = (1 + 2 + 2 + 2 * vatoms) * kFaTileBytes + (int)sizeof(FaBars) + 1024;
+  const int vatoms = vw / 64 / cg;
+  const int smem = kFaTileBytes + 2 * (kFaTileBytes / cg) + 2 * kFaTileBytes + 2 * vatoms * kFaTileBytes +
+                   (int)sizeof(FaBars) + 1024;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(flash_attn2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(flash_attn2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(flash_attn2d_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess)
       return LUN_E_ATTR;
     configured = true;
   }
   dim3 grid(N / 128, B, C / vw);
-  flash_attn2d_kernel<<<grid, kFaThreads, smem, (cudaStream_t)stream>>>(
-      tmQK, tmV, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, N, C, vw, lse_in, (__nv_bfloat16*)o_out, lse_out);
+  if (cg == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kFaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, flash_attn2d_kernel<2>, tmQK, tmK, tmV, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma,
+                           N, C, vw, lse_in, (__nv_bfloat16*)o_out, lse_out) != cudaSuccess)
+      return LUN_E_LAUNCH;
+  } else {
+    flash_attn2d_kernel<1><<<grid, kFaThreads, smem, (cudaStream_t)stream>>>(
+        tmQK, tmK, tmV, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, N, C, vw, lse_in, (__nv_bfloat16*)o_out,
+        lse_out);
+  }
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
