@@ -58,7 +58,8 @@ def test_conv_is_linear_and_stats_match_output(cuda_dev):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cin,cout,hw,stride", [(64, 128, 32, 2), (256, 256, 16, 1), (128, 64, 32, 1), (64, 32, 64, 1)])
+@pytest.mark.parametrize("cin,cout,hw,stride", [(64, 128, 32, 2), (256, 256, 16, 1), (128, 64, 32, 1), (64, 32, 64, 1),
+                                                (64, 64, 32, 1)])
 def test_per_image_statistics_of_conv_and_transposed_conv_match_output(cuda_dev, cin, cout, hw, stride):
     """The GroupNorm statistics the conv epilogue accumulates per image (LUN_EPI_STATS_IMG) equal the per-image channel
     sums / sums of squares of the stored bf16 output - for a strided 3x3 conv and for all four phases of a transposed
