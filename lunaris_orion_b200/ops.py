@@ -29,14 +29,12 @@ def _nhwc(t):
 
 # ------------------------------------------------------------------------------------------------ weight packing
 def _pack(w, transpose):
-    """fp32 [A,B,kh,kw] -> bf16 [kh*kw][A][B] (transpose False) or [kh*kw][B][A] (True): one kernel on the GPU
-    (csrc/optim.cu pack_weight_kernel), torch on the CPU (module construction / CPU-side tests only)."""
+    """fp32 [A,B,kh,kw] -> bf16 [kh*kw][A][B] (transpose False) or [kh*kw][B][A] (True): one kernel launch
+    (csrc/optim.cu pack_weight_kernel). CUDA only, like every operand of the kernels."""
     A, B, kh, kw = w.shape
-    w = w.detach()
     if not w.is_cuda:
-        t = w.permute(2, 3, 1, 0) if transpose else w.permute(2, 3, 0, 1)
-        return t.reshape(kh * kw, B if transpose else A, A if transpose else B).to(torch.bfloat16).contiguous()
-    w = w.float().contiguous()
+        raise _capi.LunarisB200Error("kernel operands are packed on the GPU: there is no CPU path")
+    w = w.detach().float().contiguous()
     out = torch.empty(kh * kw, B if transpose else A, A if transpose else B, device=w.device, dtype=torch.bfloat16)
     check(_capi.lib().lun_pack_weight_bf16(w.data_ptr(), out.data_ptr(), A, B, kh * kw, 1 if transpose else 0, _stream()),
           "lun_pack_weight_bf16")
