@@ -403,7 +403,7 @@ class _VAEFn(torch.autograd.Function):
         lib = _capi.lib()
         B = x.shape[0]
         L = vae.latent_dim
-        save = any(p.requires_grad for p in params) and torch.is_grad_enabled() or True
+        save = any(ctx.needs_input_grad)        # all False under no_grad: nothing is kept for a backward
         mulv, skips, esv = _encoder_forward(vae.encoder, x, save)
         z = torch.empty(B, L, device=x.device, dtype=torch.bfloat16)
         check(lib.lun_reparam_fwd(mulv.data_ptr(), eps.data_ptr(), z.data_ptr(), B, L, _stream()), "lun_reparam_fwd")

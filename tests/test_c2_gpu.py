@@ -7,8 +7,9 @@ zeroes gradients at the top of every micro-batch); call 4 runs on
 
 Tolerances are those of tests/test_c1_gpu.py (bf16 operands / fp32 accumulation against fp32): losses 3 % relative,
 sigmoid head means 0.05 absolute, gradient fingerprints 5 % (VAE) / 10 % (Teacher) aggregate L1, updated weights
-within one Adam step of the reference's. The advantage is (reward - EMA baseline) * 0.1, i.e. a difference of head
-means: absolute bound 0.1 * 2 * 0.05.
+within one Adam step of the reference's. The advantage is (reward - EMA baseline) * 0.1 with reward = quality mean +
+0.5 * semantic score, i.e. a difference of ill-conditioned sigmoid-head means (SURVEY.md 7 hard part 6; the C1 report
+shows the semantic head alone moving by 0.12 between fp32 and bf16): absolute bound 0.02.
 """
 import json
 import os
@@ -64,8 +65,8 @@ def test_accumulation_window_at_c2_matches_the_reference_trainer(cuda_dev, tmp_p
             assert abs(m[k] - rm[k]) <= 0.03 * drift * abs(rm[k]) + 1e-4, (i, k, m[k], rm[k])
         for k in ("quality_scores", "quality_reward"):
             assert abs(m[k] - rm[k]) <= 0.05 * drift, (i, k, m[k], rm[k])
-        assert abs(m["advantage"] - rm["advantage"]) <= 0.01 * drift, (i, m["advantage"], rm["advantage"])
-        assert abs(m["pg_loss"] - rm["pg_loss"]) <= 0.01 * drift * abs(rm["recon_loss"]) + 1e-5, (i, m["pg_loss"])
+        assert abs(m["advantage"] - rm["advantage"]) <= 0.02 * drift, (i, m["advantage"], rm["advantage"])
+        assert abs(m["pg_loss"] - rm["pg_loss"]) <= 0.02 * drift * abs(rm["recon_loss"]) + 1e-5, (i, m["pg_loss"])
         # reported losses carry the 1/accum factor (train_hybrid.py:886-896)
         assert abs(m["vae_loss"] * accum - (m["recon_loss"] + 0.1 * m["kl_loss"] + m["pg_loss"])) < 1e-3, (i, m)
         assert abs(m["vae_loss"] - rm["vae_loss"]) <= 0.03 * drift * abs(rm["vae_loss"]) + 0.01 / accum, (i, m["vae_loss"])
