@@ -33,13 +33,32 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C,
 
 constexpr int kFaThreads = 576;           // TMA warp, MMA warp, 16 softmax warps
 constexpr int kFaTileBytes = 128 * 128;   // 128 rows x 64 bf16
+// K ring depth. Pass A (row maxima: S only, 256 tensor cycles per tile) is bound by the ring's round trip
+// (S done -> k_empty -> TMA issue -> L2 latency -> k_full -> S issue, ~1300 cycles): two stages gave 690 cycles per tile.
+// A CTA of a pair holds half a K tile (8 KB) and has smem to spare; a single CTA with a 256-channel slice does not.
+__host__ __device__ constexpr int kFaKStages(int cg) { return cg == 2 ? 4 : 2; }
+// P stages. With one stage the softmax warps of tile j+1 hold their finished probabilities in registers until the PV
+// MMAs of tile j have drained the tile (11 % of the kernel's stall samples). A second stage (a CTA of a pair has the
+// 32 KB) was measured and is OFF: forward 124.5 -> 130.8 us, tensor pipe 60.0 -> 57.3 % of active cycles at C=512,
+// N=9472 (profiles/r01d_flash_attn2d.txt); the per-atom hand-off already hides most of the drain. Cause not isolated.
+constexpr int kFaPairPStages = 1;         // 2 = the measured variant
+__host__ __device__ constexpr int kFaPStages(int cg) { return cg == 2 ? kFaPairPStages : 1; }
+
+// S buffers in TMEM. Pass B double-buffers S in columns 0..255 (O lives in 256..511) and all 16 softmax warps work on
+// every tile. Pass A (row maxima only, no O yet) rotates through FOUR 128-column buffers (columns 0..511) and buffer i
+// belongs to the four warps with column quarter i, which read all 128 columns of their lane quarter: a warp then sees
+// every fourth tile, so its serial wait -> tcgen05.ld -> arrive latency (~500 cycles, twice the 256 tensor cycles of
+// an S tile) no longer paces the pass. The first PV MMA overwrites O only after every softmax warp has left pass A
+// (p_full is signalled after the named barrier that follows pass A), so the aliasing is safe.
 
 struct __align__(16) FaBars {
   uint64_t q_full;
-  uint64_t k_full[2], k_empty[2];
+  uint64_t k_full[4], k_empty[4];   // K ring: kFaKStages(CG) stages
   uint64_t v_full[2], v_empty[2];
-  uint64_t s_full[2], s_empty[2];   // S accumulators (TMEM) MMA -> softmax -> MMA
-  uint64_t p_full[2], p_empty[2];   // P tile (smem) softmax -> MMA, one pair per 64-key atom (= per softmax warp half)
+  uint64_t s_full[2], s_empty[2];   // pass B: S accumulators (TMEM) MMA -> all 16 softmax warps -> MMA
+  uint64_t sa_full[4], sa_empty[4]; // pass A: four S buffers, buffer i read by the four warps with column quarter i
+  uint64_t p_full[4], p_empty[4];   // P tile (smem) softmax -> MMA, one pair per 64-key atom (= per softmax warp half)
+                                    // and per P stage (kFaPStages): index = stage * 2 + atom
   uint64_t o_full;                  // all PV MMAs done
   uint32_t tmem_base;
   uint32_t pad;
@@ -63,9 +82,11 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
   const int vatoms = vw / 64 / CG;                  // 64-channel atoms of the value slice held by THIS CTA
   constexpr int kKBytes = kFaTileBytes / CG;        // this CTA's share of a streamed K tile: 128/CG keys
   uint8_t* sQ = smem;                               // [128][64]
-  uint8_t* sK = sQ + kFaTileBytes;                  // 2 x [128/CG][64]
-  uint8_t* sP = sK + 2 * kKBytes;                   // 2 atoms x [128 rows][64 keys]  (K-major A operand)
-  uint8_t* sV = sP + 2 * kFaTileBytes;              // 2 x vatoms x [128 keys][64 ch] (N-major B operand)
+  constexpr int KST = kFaKStages(CG);
+  uint8_t* sK = sQ + kFaTileBytes;                  // KST x [128/CG][64]
+  constexpr int PST = kFaPStages(CG);
+  uint8_t* sP = sK + KST * kKBytes;                 // PST x 2 atoms x [128 rows][64 keys]  (K-major A operand)
+  uint8_t* sV = sP + PST * 2 * kFaTileBytes;             // 2 x vatoms x [128 keys][64 ch] (N-major B operand)
   FaBars* bars = reinterpret_cast<FaBars*>(sV + 2 * vatoms * kFaTileBytes);
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
 
@@ -83,15 +104,19 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     mbar_init(&bars->q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->k_full[i], 1);
       mbar_init(&bars->k_empty[i], 1);
-      mbar_init(&bars->v_full[i], 1);
-      mbar_init(&bars->v_empty[i], 1);
-      mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->s_empty[i], 16 * CG);       // softmax warps of both CTAs report to the leader
+      mbar_init(&bars->sa_full[i], 1);
+      mbar_init(&bars->sa_empty[i], 4 * CG);
       mbar_init(&bars->p_full[i], 8 * CG);
       mbar_init(&bars->p_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->s_empty[i], 16 * CG);       // softmax warps of both CTAs report to the leader
+      mbar_init(&bars->v_full[i], 1);
+      mbar_init(&bars->v_empty[i], 1);
     }
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
@@ -110,7 +135,7 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const uint32_t tmem_s = tmem_base;                // 2 x 128 columns: S double buffer
+  const uint32_t tmem_s = tmem_base;                // 128-column S buffers: 4 in pass A (0..511), 2 in pass B (0..255)
   const uint32_t tmem_o = tmem_base + 256;          // vw (<= 256) columns: O
 
   if (warp == 0) {
@@ -123,8 +148,8 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       else tma_load_2d(sQ, &tmQK, &bars->q_full, own_col, (int)(row0 + qt * 128));
       for (int t = 0; t < steps; ++t) {
         const int j = t < first_b ? t : t - first_b;
-        const int ks = t & 1;
-        mbar_wait(&bars->k_empty[ks], ((t >> 1) & 1) ^ 1);
+        const int ks = t % KST;
+        mbar_wait(&bars->k_empty[ks], ((t / KST) & 1) ^ 1);
         if (cta_rank == 0) mbar_expect_tx(&bars->k_full[ks], kFaTileBytes);
         const int krow = (int)(row0 + j * 128 + cta_rank * (128 / CG));           // this CTA's 128/CG keys
         if (CG == 2) tma_load_2d_pair(sK + ks * kKBytes, &tmK, &bars->k_full[ks], other_col, krow);
@@ -154,18 +179,29 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       else umma_commit(bar);
     };
     mbar_wait(&bars->q_full, 0);
-    auto issue_s = [&](int t) {                      // S_t into TMEM buffer t & 1
-      const int ks = t & 1;
-      mbar_wait(&bars->k_full[ks], (t >> 1) & 1);
-      mbar_wait(&bars->s_empty[ks], ((t >> 1) & 1) ^ 1);   // the softmax warps finished reading this buffer
+    auto issue_s = [&](int t) {                      // S_t into its TMEM buffer
+      const int ks = t % KST;
+      const bool pa = t < first_b;
+      const int j = t - first_b;
+      const int sb = pa ? (t & 3) : (j & 1);
+      uint64_t* full = pa ? &bars->sa_full[sb] : &bars->s_full[sb];
+      mbar_wait(&bars->k_full[ks], (t / KST) & 1);
+      // the softmax warps finished reading this buffer
+      if (pa) {
+        mbar_wait(&bars->sa_empty[sb], ((t >> 2) & 1) ^ 1);
+      } else {
+        if (j < 2 && first_b > j)                            // last pass-A use of the TMEM columns of buffer j
+          mbar_wait(&bars->sa_empty[j], (((first_b + 3 - j) >> 2) - 1) & 1);
+        mbar_wait(&bars->s_empty[sb], ((j >> 1) & 1) ^ 1);
+      }
       tc_fence_after();
       if (elect_one()) {
         const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
         const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + ks * kKBytes), 0, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma(tmem_s + ks * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) mma(tmem_s + sb * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
         commit(&bars->k_empty[ks]);
-        commit(&bars->s_full[ks]);
+        commit(full);
       }
       __syncwarp();
     };
@@ -179,18 +215,19 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         // tile's probabilities, so the tensor pipe does not idle across the store -> fence -> barrier round trip.
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-          mbar_wait(&bars->p_full[a], j & 1);        // this atom of P written by its four softmax warps
+          const int pa = (j % PST) * 2 + a;          // P stage and atom
+          mbar_wait(&bars->p_full[pa], (j / PST) & 1);   // this atom of P written by its four softmax warps
           tc_fence_after();
           if (elect_one()) {
             // A = P atom a: K-major, 64 keys; B = V rows 64a..64a+63: N-major atoms 16 KB apart
 #pragma unroll
             for (int k = 4 * a; k < 4 * a + 4; ++k) {
-              const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + a * kFaTileBytes) + (k & 3) * 32, 0, 1024);
+              const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + pa * kFaTileBytes) + (k & 3) * 32, 0, 1024);
               const uint64_t bdesc =
                   make_smem_desc_sw128(smem_u32(sV + vsx * vatoms * kFaTileBytes) + k * 2048, kFaTileBytes, 1024);
               mma(tmem_o, adesc, bdesc, idesc_o, (j | k) != 0);
             }
-            commit(&bars->p_empty[a]);
+            commit(&bars->p_empty[pa]);
             if (a == 1) {
               commit(&bars->v_empty[vsx]);
               if (j == ntiles - 1) commit(&bars->o_full);
@@ -213,19 +250,31 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float m = -3.0e38f, l = 0.f;
-    // pass A: row max of this warp's 64 columns (no exponentials)
-    for (int t = 0; t < first_b; ++t) {
-      const int sb = t & 1;
-      mbar_wait(&bars->s_full[sb], (t >> 1) & 1);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tmem_s + sb * 128 + lane_addr + cq * 32, r);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) arrive(&bars->s_empty[sb]);
+    // pass A: row maxima (no exponentials). This warp owns S buffer cq = every fourth key tile, all 128 columns.
+    {
+      float m0 = m, m1 = m, m2 = m, m3 = m;
+      for (int t = cq; t < first_b; t += 4) {
+        mbar_wait(&bars->sa_full[cq], (t >> 2) & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(tmem_s + cq * 128 + lane_addr + h * 64, r0);
+          tmem_ld32(tmem_s + cq * 128 + lane_addr + h * 64 + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            m0 = fmaxf(m0, __uint_as_float(r0[i]));
+            m1 = fmaxf(m1, __uint_as_float(r0[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r1[i]));
+            m3 = fmaxf(m3, __uint_as_float(r1[i + 1]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive(&bars->sa_empty[cq]);
+      }
+      m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     }
     if (!dv_mode) {                                 // combine the four column quarters of every row
       bars->xch[cq][row] = m;
@@ -235,8 +284,8 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     }
     // pass B: P tiles
     for (int j = 0; j < ntiles; ++j) {
-      const int t = first_b + j, sb = t & 1;
-      mbar_wait(&bars->s_full[sb], (t >> 1) & 1);
+      const int sb = j & 1;
+      mbar_wait(&bars->s_full[sb], (j >> 1) & 1);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(tmem_s + sb * 128 + lane_addr + cq * 32, r);
@@ -269,18 +318,19 @@ flash_attn2d_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
           l += p0 + p1;                                // row sum (the bf16 rounding of P averages out over 10^3+ keys)
         }
       }
-      mbar_wait(&bars->p_empty[hf], (j & 1) ^ 1);    // this atom of the previous P consumed by the PV MMAs
+      const int pa = (j % PST) * 2 + hf;             // P stage and atom
+      mbar_wait(&bars->p_empty[pa], ((j / PST) & 1) ^ 1);   // the previous P in this stage consumed by the PV MMAs
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int chunk = (cq & 1) * 4 + g;            // 16-byte chunk (8 keys) inside the 64-key atom
-        const uint32_t addr = smem_u32(sP + hf * kFaTileBytes) + row * 128 + ((chunk ^ (row & 7)) << 4);
+        const uint32_t addr = smem_u32(sP + pa * kFaTileBytes) + row * 128 + ((chunk ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
                      "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
                      : "memory");
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) arrive(&bars->p_full[hf]);
+      if (lane == 0) arrive(&bars->p_full[pa]);
     }
     // epilogue: O / rowsum, y = gamma * O + x  (backward: dV = gamma * O); training forward also keeps O and logsumexp
     float inv_l = 1.f;
@@ -357,7 +407,7 @@ static int launch_flash(const void* qk, const void* v, const void* x, void* y, c
   rc = make_tmap_nhwc(&tmV, v, B, 1, N, C, 128, 1, 1, 1);     // {C, W=N, H=1, B}: boxes of 64 ch x 128 keys
   if (rc) return rc;
   const int vatoms = vw / 64 / cg;
-  const int smem = kFaTileBytes + 2 * (kFaTileBytes / cg) + 2 * kFaTileBytes + 2 * vatoms * kFaTileBytes +
+  const int smem = kFaTileBytes + kFaKStages(cg) * (kFaTileBytes / cg) + kFaPStages(cg) * 2 * kFaTileBytes + 2 * vatoms * kFaTileBytes +
                    (int)sizeof(FaBars) + 1024;
   static bool configured = false;
   if (!configured) {

@@ -46,7 +46,7 @@ def test_fused_losses_and_sprite_loader_match_torch(cuda_dev):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("C,HW", [(64, 16), (256, 32), (512, 16)])
+@pytest.mark.parametrize("C,HW", [(64, 16), (256, 32), (512, 16), (128, 48), (512, 48)])   # 2 / 8 / 2 / 18 / 18 key tiles
 def test_self_attention2d_flash_kernel_matches_reference_math(cuda_dev, C, HW):
     """SelfAttention2d.forward (flash-style tcgen05 kernel) vs the reference formula of lunar_generate.py:66-78 in
     fp32 on bf16-rounded operands. Tolerance: 2 % of max |ref| (bf16 q/k/v/P, fp32 accumulation)."""
@@ -77,7 +77,7 @@ def test_self_attention2d_flash_kernel_matches_reference_math(cuda_dev, C, HW):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("C,HW,B", [(64, 16, 2), (256, 32, 1), (512, 16, 3), (128, 16, 1)])
+@pytest.mark.parametrize("C,HW,B", [(64, 16, 2), (256, 32, 1), (512, 16, 3), (128, 16, 1), (256, 48, 1)])
 def test_self_attention2d_backward_matches_autograd_of_reference_math(cuda_dev, C, HW, B):
     """Gradients of SelfAttention2d (flash backward kernels: dV in the forward kernel's key-owner mode, dQ/dK in
     flash_attn2d_bwd_kernel, D/dgamma prep, 1x1-conv dgrad/wgrad) vs torch autograd of the reference formula
