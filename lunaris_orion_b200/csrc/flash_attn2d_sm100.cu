@@ -4,10 +4,11 @@
 //
 // One CTA owns 128 queries and a slice of <= 256 value channels. Q K^T is 8x cheaper than P V, so the row maximum is
 // found in a first pass over the keys (S only - no exponentials) instead of rescaling the TMEM accumulator:
-//   pass A: S = Q K_j^T per 128-key tile (tcgen05, TMEM)  -> running row max in registers
+//   pass A: S = Q K_j^T per 128-key tile (tcgen05, TMEM)  -> running row max in registers; four S buffers (the O
+//           columns are still free), buffer i read by the four softmax warps with column quarter i
 //   pass B: S again, P = exp(S - max) UNNORMALISED -> bf16 -> 128B-swizzled smem tile -> O += P V_j (O in TMEM),
 //           row sums of P accumulated alongside; the epilogue divides O by them.
-// The SFU does one exponential per score (pass B only) and everything overlaps: S is double buffered in TMEM, so the
+// The SFU does one exponential per score (pass B only) and everything overlaps: in pass B S is double buffered, so the
 // MMA warp computes S_{j+1} and runs P_j V_j while the 16 softmax warps (four per TMEM lane quarter, 32 score columns
 // each) are still exponentiating.
 // Warp roles: warp 0 = TMA producer (Q once, K / V tiles through mbarrier rings), warp 1 = MMA issuer,
