@@ -11,7 +11,6 @@ liblunaris_b200.so on NHWC bf16 tensors. Semantics are the reference's AS EXECUT
 
 There is no CPU path: calling forward on a CPU tensor raises.
 """
-import math
 
 import torch
 import torch.nn as nn

@@ -9,14 +9,12 @@ per-step cosine warm restarts on accumulation boundaries. The reward baseline li
 the reference's python float), so a step has a single device->host copy: the packed 12 metrics.
 """
 import argparse
-import math
 import os
 import time
 
 import numpy as np
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 from torch.optim.lr_scheduler import CosineAnnealingWarmRestarts
 
 from .lunar_evaluator import LunarMoETeacher

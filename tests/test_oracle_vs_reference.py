@@ -1,5 +1,4 @@
 """Pins oracle/restatement.py against the reference itself (runs only where /root/reference exists)."""
-import copy
 
 import pytest
 import torch

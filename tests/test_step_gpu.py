@@ -6,7 +6,6 @@ import pytest
 import torch
 
 import teacher_cases as tc
-from oracle import restatement as R
 
 gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.pt"),
                   weights_only=False)
