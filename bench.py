@@ -208,8 +208,8 @@ def run_ours(a):
 
 # ====================================================================================================== reference arm
 def cpu_reference(a, steps, warmup, budget_s=150.0):
-    """Oracle port of the reference's CPU path (torch fp32, all host threads): full step on batch 1 of the same
-    architecture. Returns the cpu_baseline object."""
+    """Oracle port of the reference's CPU path (torch fp32, all host threads): full steps on batch `--cpu-batch`
+    (default 4) of the same architecture, at most `budget_s` seconds of them. Returns the cpu_baseline object."""
     import torch
     from oracle import restatement as R
     from lunaris_orion_b200.lunar_evaluator import LunarMoETeacher
