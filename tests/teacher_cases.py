@@ -29,6 +29,14 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
 
 
+def fingerprint(t):
+    """sum, |sum| and 8 evenly spaced samples of a tensor - the form the golden fixtures store gradients / weights in
+    (oracle/make_golden.py::fingerprint)."""
+    t = t.detach().double().flatten().cpu()
+    idx = torch.linspace(0, t.numel() - 1, 8).long()
+    return {"sum": t.sum().item(), "abs": t.abs().sum().item(), "n": t.numel(), "samples": t[idx].float()}
+
+
 def logit(p):
     p = p.detach().double().cpu().clamp(1e-12, 1 - 1e-12)
     return torch.log(p / (1 - p))

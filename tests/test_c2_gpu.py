@@ -24,10 +24,7 @@ PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golde
 pytestmark = pytest.mark.skipif(not os.path.exists(PATH), reason="golden_c2.pt not generated")
 
 
-def _fp(t):
-    t = t.detach().double().flatten().cpu()
-    idx = torch.linspace(0, t.numel() - 1, 8).long()
-    return {"sum": t.sum().item(), "abs": t.abs().sum().item(), "n": t.numel(), "samples": t[idx].float()}
+_fp = tc.fingerprint
 
 
 @pytest.mark.gpu
