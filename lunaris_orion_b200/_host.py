@@ -1,0 +1,65 @@
+"""Host-side helpers shared by the two drop-in modules: the kernel-operand cache, the autograd guard of the
+inference-only entry points and the dropout trace used by the mask-injection parity tests."""
+import weakref
+
+import torch
+
+from ._capi import LunarisB200Error
+
+# ------------------------------------------------------------------------------------------------ operand cache
+# bf16 kernel-layout shadows of fp32 parameters. Entries hang off the parameter (or module) through weak keys, so they
+# die with the model; they are valid for one (version counter, storage address, device) of every source tensor:
+# optimizer steps bump the version, `.to()` / `p.data = w` change the address.
+_cache = weakref.WeakKeyDictionary()
+
+
+def _stamp(tensors):
+    return tuple((t._version, t.data_ptr(), str(t.device)) for t in tensors)
+
+
+def cached(owner, kind, sources, build):
+    """build() memoised per (owner, kind) while every tensor of `sources` is unchanged. `owner` is any weak-referenceable
+    object whose lifetime bounds the entry (a Parameter or a Module)."""
+    slot = _cache.get(owner)
+    if slot is None:
+        slot = _cache[owner] = {}
+    stamp = _stamp(sources)
+    ent = slot.get(kind)
+    if ent is not None and ent[0] == stamp:
+        return ent[1]
+    val = build()
+    slot[kind] = (stamp, val)
+    return val
+
+
+def cache_entries():
+    """Number of live owners (tests: entries disappear when the model is garbage collected)."""
+    return len(_cache)
+
+
+# ------------------------------------------------------------------------------------------------ autograd guard
+def require_no_grad(what, *tensors):
+    """The sub-module forwards below the two fused training entry points are inference-only: they return tensors
+    without a grad_fn. The reference back-propagates through them, so refuse instead of silently cutting the graph."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise LunarisB200Error(
+            f"{what} is inference-only in lunaris_orion_b200 (its output carries no autograd graph) but an input "
+            "requires grad. Differentiable entry points: LunarisCoreVAE.forward, LunarMoETeacher.forward (training "
+            "mode), SelfAttention2d.forward, vae_losses. Call this one under torch.no_grad() / on detached inputs.")
+
+
+# ------------------------------------------------------------------------------------------------ dropout trace
+# tests/test_dropout_parity_gpu.py rebuilds every dropout mask of a step from what the step drew: the seeds of the
+# counter-RNG elementwise dropouts and the Dropout2d / head keep-masks. None in production (one `is None` test).
+_trace = None
+
+
+def set_dropout_trace(sink):
+    """sink: list-like with .append, or None to switch the trace off. Entries: (kind, tag, value)."""
+    global _trace
+    _trace = sink
+
+
+def trace(kind, tag, value):
+    if _trace is not None:
+        _trace.append((kind, tag, value))

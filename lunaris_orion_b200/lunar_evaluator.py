@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _capi, ops
+from . import _capi, _host, ops
 from ._capi import check
 
 _HEADS = 8
@@ -52,6 +52,7 @@ class PixelArtFeatureExtractor(nn.Module):
         self.fusion = _conv_act_bn(64 * 3, feature_dim, 1, 0)
 
     def forward(self, x):
+        _host.require_no_grad("PixelArtFeatureExtractor.forward", x)
         feats, _ = _fe_forward(self, x, 1)
         return _to_nchw(feats, x.shape[0], x.shape[2], x.shape[3])
 
@@ -87,10 +88,11 @@ class PixelArtAttention(nn.Module):
             self.last_spatial_shapes = torch.tensor([H, W], device=device)
 
     def forward(self, x):
+        _host.require_no_grad("PixelArtAttention.forward", x)
         B, C, H, W = x.shape
         one, zero = torch.ones(C, device=x.device), torch.zeros(C, device=x.device)
         h2, _ = _attention_forward(self, _to_nhwc(x).view(B, H * W, C), one, zero, None, B, H, W, self.training,
-                                   save=False)
+                                   save=False, tag="attention")
         return _to_nchw(h2, B, H, W)
 
 
@@ -113,8 +115,9 @@ class ExpertBlock(nn.Module):
         self.layer_scale = nn.Parameter(torch.ones(1, out_channels, 1, 1) * layer_scale_init)
 
     def forward(self, x):
+        _host.require_no_grad("ExpertBlock.forward", x)
         B, C, H, W = x.shape
-        out, _ = _block_forward(self, _to_nhwc(x), B, H, W, self.training, 1, save=False, pool=None)
+        out, _ = _block_forward(self, _to_nhwc(x), B, H, W, self.training, 1, save=False, pool=None, tag="block")
         return _to_nchw(out, B, H, W)
 
 
@@ -164,25 +167,38 @@ class LunarMoETeacher(nn.Module):
             nn.init.zeros_(m.bias)
 
     def forward(self, x, prompt_embedding=None):
+        """Same contract as lunar_evaluator.py:409-462. Differentiable in training mode (the reference's executed
+        gradient set); in eval mode the outputs are returned without an autograd graph."""
         if not x.is_cuda:
             raise _capi.LunarisB200Error("lunaris_orion_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        _host.require_no_grad("LunarMoETeacher.forward w.r.t. its input (the reference's reentrant checkpoints would "
+                              "then produce a different gradient set; pass x.detach())", x)
+        grad_on = torch.is_grad_enabled() and self.training
+        if grad_on and not self.use_checkpointing:
+            raise _capi.LunarisB200Error(
+                "LunarMoETeacher(use_checkpointing=False) in training mode under autograd is not implemented: without "
+                "the reentrant checkpoints the reference back-propagates into the feature extractor, conv1 and qkv "
+                "(a different gradient set from the one this path reproduces). Use use_checkpointing=True.")
+        if not grad_on and torch.is_grad_enabled():
+            _warn_once("LunarMoETeacher.forward in eval mode returns outputs without an autograd graph "
+                       "(the reference would back-propagate through them); wrap the call in torch.no_grad().")
         B, _, H, W = x.shape
         hw = float(H * W)
-        grad_on = torch.is_grad_enabled() and self.training
         params = _trunk_grad_params(self) if grad_on else []
         res = _TeacherTrunk.apply(self, x.detach(), grad_on, *params)
         pooled_fe, pooled = res[0], res[1:1 + self.num_experts]
         fmaps = res[1 + self.num_experts:]
 
-        with torch.autocast("cuda", enabled=False):
-            weights = self.gate[2:](pooled_fe / hw)                               # Linear..Softmax on pooled feats
+        with torch.autocast("cuda", enabled=False), torch.set_grad_enabled(grad_on):
+            weights = torch.softmax(_mlp_head(self.gate, pooled_fe / hw, False, self.training, "gate_drop"), dim=1)
             means = [p / hw for p in pooled]
-            quals = [self.quality_heads[e][2:](means[e]) for e in range(self.num_experts)]
+            quals = [_mlp_head(self.quality_heads[e], means[e], True, self.training, f"quality_drop.{e}")
+                     for e in range(self.num_experts)]
             wq = (torch.stack(quals, 1) * weights.unsqueeze(-1)).sum(1)
             comb = (torch.stack(means, 1) * weights.unsqueeze(-1)).sum(1)
-            style = self.style_net[2:](comb)
-            prompt = self.prompt_net[2:](comb)
-            sem = self.semantic_head[2:](means[0])
+            style = _mlp_head(self.style_net, comb, True, self.training, "style_drop")
+            prompt = _mlp_head(self.prompt_net, comb, True, self.training, "prompt_drop")
+            sem = torch.sigmoid(_mlp_head(self.semantic_head, means[0], True, self.training, "semantic_drop"))
             sem = sem * F.cosine_similarity(prompt, prompt.detach(), dim=1).unsqueeze(1)
         return {
             'quality_scores': torch.sigmoid(wq),
@@ -194,6 +210,34 @@ class LunarMoETeacher(nn.Module):
         }
 
 
+def _mlp_head(seq, pooled, ln, training, tag):
+    """[LayerNorm] -> Linear -> LeakyReLU -> Dropout -> Linear of a head's nn.Sequential on pooled [B,C] features
+    (lunar_evaluator.py:353-397; module indices: gate 2,5 - the others 2,3,6). The Dropout keep-mask is drawn
+    explicitly (and offered to the dropout trace) instead of through nn.Dropout."""
+    if ln:
+        h = F.layer_norm(pooled, pooled.shape[-1:], seq[2].weight, seq[2].bias, seq[2].eps)
+        l1, drop, l2 = seq[3], seq[5], seq[6]
+    else:
+        h = pooled
+        l1, drop, l2 = seq[2], seq[4], seq[5]
+    h = F.leaky_relu(F.linear(h, l1.weight, l1.bias), _SLOPE)
+    if training and drop.p > 0:
+        keep = torch.empty_like(h).bernoulli_(1.0 - drop.p).mul_(1.0 / (1.0 - drop.p))
+        _host.trace("mask", tag, keep)
+        h = h * keep
+    return F.linear(h, l2.weight, l2.bias)
+
+
+_warned = set()
+
+
+def _warn_once(msg):
+    if msg not in _warned:
+        _warned.add(msg)
+        import warnings
+        warnings.warn(msg, stacklevel=3)
+
+
 # ====================================================================================================== plumbing
 def _to_nhwc(x):
     return x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
@@ -203,40 +247,34 @@ def _to_nchw(y, B, H, W):
     return y.view(B, H, W, -1).permute(0, 3, 1, 2).float()
 
 
-_pack_cache = {}
-
-
 def _packed(param, kind):
-    """bf16 kernel-layout shadow of an fp32 parameter, refreshed when the optimizer changes it in place."""
-    key = (id(param), kind)
-    ent = _pack_cache.get(key)
-    ver = param._version
-    if ent is not None and ent[0] == ver and ent[1].device == param.device and ent[2] is param:
-        return ent[1]
-    if kind == "fwd":
-        t = ops.pack_conv_weight(param)
-    elif kind == "dgrad":
-        t = ops.pack_conv_weight_dgrad(param)
-    elif kind == "f32":
-        t = param.detach().float().contiguous()
-    elif kind in ("q_fwd", "kv_fwd"):            # qkv conv weight [3C, C, 1, 1] split into its Q and K|V row blocks
-        C = param.shape[1]
-        rows = param.detach()[:C] if kind == "q_fwd" else param.detach()[C:]
-        t = ops.pack_conv_weight(rows)
-    elif kind in ("q_f32", "kv_f32"):            # qkv bias [3C]
-        C = param.shape[0] // 3
-        t = (param.detach()[:C] if kind == "q_f32" else param.detach()[C:]).float().contiguous()
-    else:
+    """bf16 kernel-layout shadow of an fp32 parameter (cached on the parameter; refreshed when the optimizer changes
+    it in place or its storage moves, see _host.cached)."""
+    def build():
+        if kind == "fwd":
+            return ops.pack_conv_weight(param)
+        if kind == "dgrad":
+            return ops.pack_conv_weight_dgrad(param)
+        if kind == "f32":
+            return param.detach().float().contiguous()
+        if kind in ("q_fwd", "kv_fwd"):          # qkv conv weight [3C, C, 1, 1] split into its Q and K|V row blocks
+            C = param.shape[1]
+            return ops.pack_conv_weight(param.detach()[:C] if kind == "q_fwd" else param.detach()[C:])
+        if kind in ("q_f32", "kv_f32"):          # qkv bias [3C]
+            C = param.shape[0] // 3
+            return (param.detach()[:C] if kind == "q_f32" else param.detach()[C:]).float().contiguous()
         raise KeyError(kind)
-    _pack_cache[key] = (ver, t, param)
-    return t
+    return _host.cached(param, kind, (param,), build)
 
 
 _stream = _capi.raw_stream
 
 
-def _cpu_seed():
-    return int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
+def _cpu_seed(tag):
+    """Seed of one counter-RNG dropout launch, drawn from torch's CPU generator (rank r is seeded with seed + r)."""
+    seed = int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
+    _host.trace("seed", tag, seed)
+    return seed
 
 
 def _p(t):
@@ -269,9 +307,10 @@ def _affine(x, B, HW, C, scale, shift, mask2d=None, ls=None, identity=None, id_s
     return y
 
 
-def _drop2d_mask(B, C, p, device):
+def _drop2d_mask(B, C, p, device, tag):
     """Dropout2d keep-mask [B,C]: 0 or bf16(1/(1-p)) (what the reference's bf16 feature_dropout multiplies by)."""
     keep = torch.empty(B, C, device=device, dtype=torch.float32).bernoulli_(1.0 - p)
+    _host.trace("mask2d", tag, keep)
     return keep * float(torch.tensor(1.0 / (1.0 - p)).to(torch.bfloat16))
 
 
@@ -311,7 +350,7 @@ def _fe_forward(fe, x, n_updates):
         aff = [_bn_eval(br[3]) for br in branches]
     scale = torch.cat([a[0] for a in aff]).contiguous()
     shift = torch.cat([a[1] for a in aff]).contiguous()
-    cat_n = _affine(cat, B, HW, 192, scale, shift, seed=_cpu_seed() if p_drop > 0 else 0, drop_p=p_drop)
+    cat_n = _affine(cat, B, HW, 192, scale, shift, seed=_cpu_seed("fe_drop") if p_drop > 0 else 0, drop_p=p_drop)
 
     cf, bnf = fe.fusion[0], fe.fusion[2]
     C = cf.out_channels
@@ -324,36 +363,29 @@ def _fe_forward(fe, x, n_updates):
     return feats, pooled
 
 
-_fold_cache = {}
-
-
 def _folded_attention_weights(att):
     """Weight-only precompute for the K/V-free attention (refreshed when qkv changes; in reference mode it never
     does - qkv receives no gradient): Mq [8C, C] = Wk_h^T Wq_h / sqrt(hd) stacked over heads, cq [8C] = Wk_h^T bq_h /
-    sqrt(hd), and the value projection as a block-diagonal [C, 8C] matrix. bf16 operands, fp32 products."""
+    sqrt(hd), and the value projection per head Wv [h][hd][C]. bf16 operands, fp32 products."""
     w, bq = att.qkv.weight, att.qkv.bias
-    key = id(att)
-    ver = (w._version, bq._version, str(w.device))
-    ent = _fold_cache.get(key)
-    if ent is not None and ent[0] == ver and ent[2] is att:     # identity check: ids are recycled after GC
-        return ent[1]
-    C, h = att.qkv.in_channels, att.num_heads
-    hd = C // h
-    wf = w.detach().reshape(3, h, hd, C).to(torch.bfloat16).float()          # [3][head][d][c]
-    bf = bq.detach().reshape(3, h, hd).float()
-    scale = float(torch.tensor(hd ** -0.5).to(torch.bfloat16))
-    mq = torch.einsum("hdk,hdc->hkc", wf[1], wf[0]).mul_(scale).reshape(h * C, C)
-    cq = torch.einsum("hdk,hd->hk", wf[1], bf[0]).mul_(scale).reshape(h * C)
-    wv = torch.zeros(C, h * C, device=w.device)
-    for i in range(h):
-        wv[i * hd:(i + 1) * hd, i * C:(i + 1) * C] = wf[2, i]
-    out = (mq.to(torch.bfloat16).contiguous(), cq.contiguous(), wv.to(torch.bfloat16).contiguous(),
-           bf[2].reshape(C).contiguous())
-    _fold_cache[key] = (ver, out, att)
-    return out
+
+    def build():
+        C, h = att.qkv.in_channels, att.num_heads
+        hd = C // h
+        wf = w.detach().reshape(3, h, hd, C).to(torch.bfloat16).float()          # [3][head][d][c]
+        bf = bq.detach().reshape(3, h, hd).float()
+        scale = float(torch.tensor(hd ** -0.5).to(torch.bfloat16))
+        mq = torch.einsum("hdk,hdc->hkc", wf[1], wf[0]).mul_(scale).reshape(h * C, C)
+        cq = torch.einsum("hdk,hd->hk", wf[1], bf[0]).mul_(scale).reshape(h * C)
+        wv = torch.zeros(C, h * C, device=w.device)
+        for i in range(h):
+            wv[i * hd:(i + 1) * hd, i * C:(i + 1) * C] = wf[2, i]
+        return (mq.to(torch.bfloat16).contiguous(), cq.contiguous(), wv.to(torch.bfloat16).contiguous(),
+                bf[2].reshape(C).contiguous())
+    return _host.cached(att, "fold", (w, bq), build)
 
 
-def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save):
+def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save, tag):
     """PixelArtAttention.forward as executed (lunar_evaluator.py:189-227) on the pre-BatchNorm conv1 output y1
     [B,HW,C] (x1 = drop2d(bn(y1)) is applied on load, never written). Only N/32+31 rows survive the reference's
     chunk-index scatter; for those rows the K and V projections are folded into the query / output side (see
@@ -379,16 +411,17 @@ def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save):
     if nq_pad > nq:
         xbar[:, nq:].zero_()
     xbar = xbar.view(B * nq_pad, heads * C)
+    seed_attn = _cpu_seed(tag + ".attn_drop") if p_attn > 0 else 0
     check(lib.lun_attn_fold_rows_bf16(y1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), _p(m1), qt.data_ptr(),
-                                      xbar.data_ptr(), B, HW, C, heads, nq_pad, _cpu_seed() if p_attn > 0 else 0,
-                                      float(p_attn), _stream()), "lun_attn_fold_rows_bf16")
+                                      xbar.data_ptr(), B, HW, C, heads, nq_pad, seed_attn, float(p_attn), _stream()),
+          "lun_attn_fold_rows_bf16")
     att_small = ops.linear_fprop(xbar, wv_bd, bv, out_f32=False).view(B, nq_pad, C)
     if nq_pad > nq:
         att_small[:, nq:].zero_()
     wp = _packed(att.proj.weight, "fwd")
     proj_small = ops.linear_fprop(att_small.view(B * nq_pad, C), wp.view(C, C), _packed(att.proj.bias, "f32"),
                                   out_f32=False)
-    seed = _cpu_seed() if p_proj > 0 else 0
+    seed = _cpu_seed(tag + ".proj_drop") if p_proj > 0 else 0
     h2 = torch.empty(B, HW, C, device=y1.device, dtype=torch.bfloat16)
     check(lib.lun_proj_expand_bf16(proj_small.data_ptr(), _packed(att.proj.bias, "f32").data_ptr(), h2.data_ptr(), B,
                                    HW, C, nq, nq_pad, seed, float(p_proj), _stream()), "lun_proj_expand_bf16")
@@ -396,7 +429,7 @@ def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save):
     return h2, saved
 
 
-def _block_forward(blk, x, B, H, W, training, n_updates, save, pool):
+def _block_forward(blk, x, B, H, W, training, n_updates, save, pool, tag):
     """ExpertBlock.forward (lunar_evaluator.py:260-275) on NHWC bf16 x [B,HW,Cin]. Returns (out [B,HW,C], saved)."""
     HW = H * W
     dev = x.device
@@ -409,8 +442,8 @@ def _block_forward(blk, x, B, H, W, training, n_updates, save, pool):
     y1 = ops.conv2d_fprop(x.view(B, H, W, Cin), _packed(c1.weight, "fwd"), 3, 1, 1, bias=_packed(c1.bias, "f32"),
                           act_leaky=True, stats=st, slope=_SLOPE)
     sc1, sh1 = _bn_train(bn1, st, B * HW, n_updates)[:2] if training else _bn_eval(bn1)
-    m1 = _drop2d_mask(B, C, p2d, dev) if p2d > 0 else None
-    h2, att_saved = _attention_forward(blk.attention, y1.view(B, HW, C), sc1, sh1, m1, B, H, W, training, save)
+    m1 = _drop2d_mask(B, C, p2d, dev, tag + ".drop2d_1") if p2d > 0 else None
+    h2, att_saved = _attention_forward(blk.attention, y1.view(B, HW, C), sc1, sh1, m1, B, H, W, training, save, tag)
     del y1
 
     st = torch.zeros(2 * C, device=dev) if training else None
@@ -420,7 +453,7 @@ def _block_forward(blk, x, B, H, W, training, n_updates, save, pool):
         sc2, sh2, mean2, rstd2 = _bn_train(bn2, st, B * HW, n_updates)
     else:
         (sc2, sh2), mean2, rstd2 = _bn_eval(bn2), None, None
-    m2 = _drop2d_mask(B, C, d2.p, dev) if training and d2.p > 0 else None
+    m2 = _drop2d_mask(B, C, d2.p, dev, tag + ".drop2d_2") if training and d2.p > 0 else None
 
     has_sc = not isinstance(blk.shortcut, nn.Identity)
     if has_sc:
@@ -489,7 +522,7 @@ class _TeacherTrunk(torch.autograd.Function):
         training = teacher.training
         feats, pooled_fe = _fe_forward(teacher.feature_extractor, x, 1)
         pooled, fmaps, saved = [], [], []
-        for expert in teacher.experts:
+        for e, expert in enumerate(teacher.experts):
             h = feats
             per = []
             C = expert[0].conv1[0].out_channels
@@ -498,7 +531,8 @@ class _TeacherTrunk(torch.autograd.Function):
                 pool = torch.zeros(B, C, device=x.device) if last else None
                 # blocks whose checkpoint segment the reference re-runs in backward update BN stats twice
                 recomputed = grad_on and b > 0
-                h, sv = _block_forward(blk, h, B, H, W, training, 2 if recomputed else 1, save=grad_on, pool=pool)
+                h, sv = _block_forward(blk, h, B, H, W, training, 2 if recomputed else 1, save=grad_on, pool=pool,
+                                       tag=f"experts.{e}.{b}")
                 per.append(sv)
                 if last:
                     pooled.append(pool)

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _capi, ops
+from . import _capi, _host, ops
 from ._capi import check
 
 
@@ -33,7 +33,19 @@ class ResBlock(nn.Module):
             else nn.Identity()
 
     def forward(self, x):
-        raise _capi.LunarisB200Error("ResBlock runs only inside LunarisCoreVAE's fused forward")
+        """mish(conv2(conv1(x)) + shortcut(x)) (lunar_generate.py:47-53), incl. the 1x1 shortcut conv of the
+        in != out case. Inference-only as a standalone module (the VAE's fused forward / backward is the
+        differentiable path)."""
+        if not x.is_cuda:
+            raise _capi.LunarisB200Error("lunaris_orion_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        _host.require_no_grad("ResBlock.forward", x)
+        B, cin, H, W = x.shape
+        C = self.conv1[0].out_channels
+        if H != W or cin % 64 or C % 64:
+            raise _capi.LunarisB200Error("ResBlock kernel needs square maps and channel counts that are multiples of 64")
+        a = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).view(B, H * W, cin)
+        out, _ = _resblock_forward(self, a, B, H, C, save=False)
+        return out.view(B, H, W, C).permute(0, 3, 1, 2).float()
 
 
 class SelfAttention2d(nn.Module):
@@ -94,15 +106,14 @@ class _SelfAttention2dFn(torch.autograd.Function):
         check(_capi.lib().lun_flash_attn2d_bf16(qk.data_ptr(), v.data_ptr(), xf.data_ptr(), y.data_ptr(), gm.data_ptr(),
                                                 B, N, C, _p(o), _p(lse), _stream()), "lun_flash_attn2d_bf16")
         if need:
-            ctx.saved = (xf, qk, v, o, lse, wqk, wv, gm.clone())
+            ctx.save_for_backward(xf, qk, v, o, lse, wqk, wv, gm.clone())
             ctx.dims = (B, C, H, W)
         return y.view(B, H, W, C).permute(0, 3, 1, 2).float()
 
     @staticmethod
     def backward(ctx, dy):
         lib = _capi.lib()
-        xf, qk, v, o, lse, wqk, wv, gm = ctx.saved
-        ctx.saved = None
+        xf, qk, v, o, lse, wqk, wv, gm = ctx.saved_tensors
         B, C, H, W = ctx.dims
         N, dq = H * W, C // 8
         dev = dy.device
@@ -144,6 +155,7 @@ class Encoder(nn.Module):
         self.fc_logvar = nn.Linear(512 * 8 * 8, latent_dim)
 
     def forward(self, x):
+        _host.require_no_grad("Encoder.forward", x)
         mulv, skips, _ = _encoder_forward(self, x, save=False)
         L = self.fc_mu.out_features
         B = x.shape[0]
@@ -166,6 +178,7 @@ class Decoder(nn.Module):
         self.final_conv = nn.Conv2d(32, 3, kernel_size=3, padding=1)
 
     def forward(self, z, skips):
+        _host.require_no_grad("Decoder.forward", z, *skips)
         B = z.shape[0]
         sk = [s.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).view(B, -1, s.shape[1]) for s in skips]
         recon, _ = _decoder_forward(self, z.detach().to(torch.bfloat16).contiguous(), sk, save=False)
@@ -203,18 +216,9 @@ class LunarisCoreVAE(nn.Module):
 
 
 # ====================================================================================================== plumbing
-_cache = {}
-
-
 def _cached(key_params, kind, build):
-    key = (kind,) + tuple(id(p) for p in key_params)
-    vers = tuple(p._version for p in key_params)
-    ent = _cache.get(key)
-    if ent is not None and ent[0] == vers and ent[2][0] is key_params[0] and ent[1].device == key_params[0].device:
-        return ent[1]
-    t = build()
-    _cache[key] = (vers, t, key_params)
-    return t
+    """Kernel-layout shadow of one or more parameters, cached on the first of them (see _host.cached)."""
+    return _host.cached(key_params[0], kind, key_params, build)
 
 
 def _f32(p):
@@ -299,16 +303,25 @@ def _colsum(t, P, C):
 
 # ====================================================================================================== forward
 def _resblock_forward(rb, a, B, hw, C, save):
-    """ResBlock.forward (lunar_generate.py:47-53) on NHWC bf16 a [B,HW,C]."""
+    """ResBlock.forward (lunar_generate.py:47-53) on NHWC bf16 a [B,HW,Cin]; C = out channels. The 1x1 shortcut conv
+    of the in != out case (never instantiated by the VAE, whose blocks have in == out) is forward-only."""
     HW = hw * hw
     c1, g1 = rb.conv1[0], rb.conv1[1]
     c2, g2 = rb.conv2[0], rb.conv2[1]
-    t1, s1 = _conv_gn(B, hw, C, a.device, lambda st: ops.conv2d_fprop(a.view(B, hw, hw, C), _wfwd(c1), 3, 1, 1,
+    cin = c1.in_channels
+    if isinstance(rb.shortcut, nn.Identity):
+        ident = a
+    else:
+        if save:
+            raise _capi.LunarisB200Error("ResBlock with a 1x1 shortcut conv has no backward in lunaris_orion_b200")
+        ident = ops.conv2d_fprop(a.view(B, hw, hw, cin), _wfwd(rb.shortcut), 1, 1, 0,
+                                 bias=_f32(rb.shortcut.bias)).view(B, HW, C)
+    t1, s1 = _conv_gn(B, hw, C, a.device, lambda st: ops.conv2d_fprop(a.view(B, hw, hw, cin), _wfwd(c1), 3, 1, 1,
                                                                       bias=_f32(c1.bias), img_stats=st))
     r1 = _gn_mish(t1, s1, g1, B, HW, C)
     t2, s2 = _conv_gn(B, hw, C, a.device, lambda st: ops.conv2d_fprop(r1.view(B, hw, hw, C), _wfwd(c2), 3, 1, 1,
                                                                       bias=_f32(c2.bias), img_stats=st))
-    out = _gn_mish(t2, s2, g2, B, HW, C, res=a)
+    out = _gn_mish(t2, s2, g2, B, HW, C, res=ident)
     return out, (dict(a=a, t1=t1, s1=s1, r1=r1, t2=t2, s2=s2) if save else None)
 
 
@@ -409,7 +422,8 @@ class _VAEFn(torch.autograd.Function):
         check(lib.lun_reparam_fwd(mulv.data_ptr(), eps.data_ptr(), z.data_ptr(), B, L, _stream()), "lun_reparam_fwd")
         recon, dsv = _decoder_forward(vae.decoder, z, skips, save)
         ctx.vae, ctx.esv, ctx.dsv = vae, esv, dsv
-        ctx.x, ctx.eps, ctx.mulv, ctx.recon = x, eps, mulv, recon
+        if save:
+            ctx.save_for_backward(x, eps, mulv, recon)     # recon is an output: saved through autograd, no cycle
         ctx.names = [n for n, _ in vae.named_parameters()]
         mu, logvar = mulv[:, :L], mulv[:, L:]
         return recon, mu, logvar
@@ -419,7 +433,7 @@ class _VAEFn(torch.autograd.Function):
         lib = _capi.lib()
         vae, esv, dsv = ctx.vae, ctx.esv, ctx.dsv
         enc, dec = vae.encoder, vae.decoder
-        x, eps, mulv, recon = ctx.x, ctx.eps, ctx.mulv, ctx.recon
+        x, eps, mulv, recon = ctx.saved_tensors
         B, L = x.shape[0], vae.latent_dim
         dev = x.device
         g = {}
