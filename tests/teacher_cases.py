@@ -42,6 +42,13 @@ def logit(p):
     return torch.log(p / (1 - p))
 
 
+def logit_c(p=None, logits=None, lim=12.0):
+    """Logit clamped to +-lim: an fp32 probability cannot resolve logits beyond ~+-15 (1 - p underflows the spacing
+    of floats near 1), so saturated heads are compared on the clamped scale. Pass probabilities or raw logits."""
+    z = logit(p) if logits is None else logits.detach().double().cpu()
+    return z.clamp(-lim, lim)
+
+
 def eval_report(dev, B=2):
     t = make_teacher(dev).eval()
     sd = oracle_sd(t)
@@ -163,3 +170,42 @@ def trunk_report(dev, B=2, feat=64, calibrate=True):
         rep["cal_grad_rel_max"] = max(ce.values())
         rep["cal_grad_worst"] = sorted(ce.items(), key=lambda kv: -kv[1])[:5]
     return rep
+
+
+def fingerprint_k(t, k):
+    """fingerprint() with k samples (golden_c3.pt keeps 64 per tensor, oracle/make_golden_c3.py)."""
+    t = t.detach().double().flatten().cpu()
+    idx = torch.linspace(0, t.numel() - 1, min(k, t.numel())).long()
+    return {"sum": t.sum().item(), "abs": t.abs().sum().item(), "n": t.numel(), "samples": t[idx].float()}
+
+
+def sample_agreement(named_tensors, ref_fps, skip=("shortcut.0.bias",)):
+    """Value / sign agreement between tensors of the CUDA path and the golden fingerprints' evenly spaced samples.
+    Returns the cosine between the two pooled sample vectors (each tensor normalised by the reference's mean |g| so
+    that small tensors count), the fraction of significant samples (|ref| above 10 % of the tensor's mean |ref|) whose
+    sign agrees, and the fraction of samples within 10 % of |ref| + 10 % of the tensor's mean |ref|.
+    Tensors whose exact value is zero (`skip`: conv biases feeding a train-mode BatchNorm) hold rounding noise only."""
+    mine, ref, sign_ok, sign_n, val_ok, val_n = [], [], 0, 0, 0, 0
+    per = {}
+    for name, t in named_tensors:
+        if name not in ref_fps or any(name.endswith(s) for s in skip):
+            continue
+        r = ref_fps[name]
+        k = r["samples"].numel()
+        o = fingerprint_k(t, k)["samples"].double()
+        rs = r["samples"].double()
+        scale = r["abs"] / r["n"] + 1e-30
+        mine.append(o / scale)
+        ref.append(rs / scale)
+        sig = rs.abs() > 0.1 * scale
+        ok = int((torch.sign(o[sig]) == torch.sign(rs[sig])).sum())
+        sign_ok += ok
+        sign_n += int(sig.sum())
+        v = (o - rs).abs() <= 0.1 * rs.abs() + 0.1 * scale
+        val_ok += int(v.sum())
+        val_n += k
+        per[name] = float(((o - rs).abs().max() / (rs.abs().max() + 1e-30)))
+    a, b = torch.cat(mine), torch.cat(ref)
+    return {"cosine": float((a @ b) / (a.norm() * b.norm() + 1e-30)), "sign_agree": sign_ok / max(sign_n, 1),
+            "n_significant": sign_n, "value_within_10pct": val_ok / max(val_n, 1), "n_samples": val_n,
+            "worst_tensor": max(per.items(), key=lambda kv: kv[1])}

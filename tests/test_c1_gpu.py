@@ -68,20 +68,25 @@ def test_two_trainer_steps_at_c1_match_the_reference_trainer(cuda_dev, tmp_path)
             per[n] = abs(o["abs"] - r["abs"]) / (r["abs"] + 1e-30)
         worst[name] = {"aggregate_l1": num / den, "worst_tensor": max(per.items(), key=lambda kv: kv[1])}
     report["grads"] = worst
-    # parameters after clip + AdamW: Adam's first step moves every element by ~lr regardless of gradient scale, so
-    # the updated weights pin the SIGN pattern of the gradients; compare the fingerprints' samples
-    moved = {}
-    for name, model, key in (("vae", tm.vae, "vae_params_after"), ("teacher", tm.teacher, "teacher_params_after")):
+    # value / sign agreement of the fingerprints' gradient samples, and the parameters after clip + AdamW: Adam's first
+    # step moves every element by lr * sign(g), so a sample further than ONE lr from the reference's updated value
+    # stepped in the opposite direction (a fully sign-flipped gradient would put every sample 2 lr away)
+    agree, flips = {}, {}
+    for name, model, key, pkey in (("vae", tm.vae, "vae_grads", "vae_params_after"),
+                                   ("teacher", tm.teacher, "teacher_grads", "teacher_params_after")):
+        agree[name] = tc.sample_agreement(((n, p.grad) for n, p in model.named_parameters() if p.grad is not None),
+                                          ref0[key])
         bad = tot = 0
+        lr = ref0["vae_lr" if name == "vae" else "teacher_lr"]
         for n, p in model.named_parameters():
-            if n not in ref0[key]:
+            if n not in ref0[pkey] or n.endswith("shortcut.0.bias"):
                 continue
-            d = (_fp(p)["samples"] - ref0[key][n]["samples"]).abs()
-            lr = ref0["vae_lr" if name == "vae" else "teacher_lr"]
-            bad += int((d > 2.5 * lr + 1e-7).sum())          # > one full opposite-sign Adam step (2 lr) + slack
+            d = (_fp(p)["samples"] - ref0[pkey][n]["samples"]).abs()
+            bad += int((d > 1.0 * lr).sum())
             tot += d.numel()
-        moved[name] = bad / tot
-    report["param_samples_off_by_more_than_one_adam_step"] = moved
+        flips[name] = bad / tot
+    report["grad_sample_agreement"] = agree
+    report["param_samples_stepped_in_opposite_direction"] = flips
 
     m1 = tm._process_batch(x, 1)
     ref1 = gold["step1"]
@@ -92,7 +97,10 @@ def test_two_trainer_steps_at_c1_match_the_reference_trainer(cuda_dev, tmp_path)
 
     assert worst["vae"]["aggregate_l1"] < 0.05, worst
     assert worst["teacher"]["aggregate_l1"] < 0.10, worst
-    assert moved["vae"] == 0.0 and moved["teacher"] == 0.0, moved
+    for name in ("vae", "teacher"):
+        assert agree[name]["cosine"] > 0.99, agree
+        assert agree[name]["sign_agree"] > 0.97, agree
+        assert flips[name] < 0.04, flips
     # second step runs on the UPDATED weights (optimizer boundary + schedule in the loop)
     for k in ("recon_loss", "kl_loss", "vae_loss"):
         assert abs(m1[k] - ref1["metrics"][k]) <= 0.03 * abs(ref1["metrics"][k]) + 1e-4, (k, m1[k], ref1["metrics"][k])
@@ -115,3 +123,35 @@ def test_two_trainer_steps_at_c1_match_the_reference_trainer(cuda_dev, tmp_path)
         sd = tm.teacher.state_dict()
         for k, v in ref2["teacher_nbt"].items():
             assert int(sd[k]) == v, k
+
+
+@pytest.mark.gpu
+def test_semantic_and_quality_logits_at_c1_within_bf16_calibration(cuda_dev):
+    """`semantic_score` / `quality_scores` come from kaiming-fan_out MLPs on LayerNormed pooled features: logits of
+    magnitude >> 1 whose sigmoid saturates (SURVEY.md 7 hard part 6), so the step metrics `semantic_reward` /
+    `quality_reward` cannot be compared as probabilities. Here the pre-sigmoid logits of a train-mode forward at the
+    C1 size (batch 8, feat 256, emb 128) are compared per sample with the fp32 CPU oracle, and the bound is 3x what the
+    SAME oracle loses when executed under bf16 autocast on this GPU (+ a floor of 2 % of the logit scale)."""
+    from oracle import restatement as R
+    B, feat, emb = 8, 256, 128
+    t = tc.make_teacher(cuda_dev, feat=feat, emb=emb, dropout=0.0, seed=42).train()
+    sd, sd_cal = tc.oracle_sd(t), tc.oracle_sd(t)
+    x = tc.images(B, seed=11)
+    with torch.no_grad():
+        out = t(x.to(cuda_dev))
+        ref = R.teacher_forward(x, sd, training=True, no_grad_pass=True)
+        sdc = {k: v.detach().to(cuda_dev) for k, v in sd_cal.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            cal = R.teacher_forward(x.to(cuda_dev), sdc, training=True, no_grad_pass=True)
+    rep = {}
+    for name, mine, key in (("semantic", out["semantic_score"], "semantic_logit"),
+                            ("quality", out["quality_scores"], "quality_logits")):
+        r = tc.logit_c(logits=ref[key])
+        d_mine = (tc.logit_c(mine) - r).abs().max().item()
+        d_cal = (tc.logit_c(logits=cal[key]) - r).abs().max().item()
+        rep[name] = {"mine": d_mine, "calibration": d_cal, "scale": r.abs().max().item()}
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        json.dump(rep, open(os.path.join(out_dir, "c1_logit_calibration.json"), "w"), indent=1)
+    for name, r in rep.items():
+        assert r["mine"] <= 3 * r["calibration"] + 0.02 * r["scale"] + 0.02, (name, r)

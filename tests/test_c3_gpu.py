@@ -1,0 +1,164 @@
+"""Parity AT THE BENCHMARKED SHAPES (BASELINE.json configs[2], "C3": latent 512 / emb 256 / feat 512, head_dim 64).
+
+(1) Two trainer steps of lunaris_orion_b200.train_hybrid.TrainingManager vs tests/golden/golden_c3.pt - what the
+    UNMODIFIED reference trainer produced on CPU fp32 for the same seeds on a bounded batch of 4
+    (oracle/make_golden_c3.py): 12 metrics per step, per-sample head outputs compared as logits, grad-None set,
+    BatchNorm counters, schedule, and value / sign agreement of 64 samples of every gradient tensor.
+(2) The Teacher trunk forward + backward at feat 512 against the oracle, elementwise on all 100 live gradient
+    tensors, within the bf16-autocast calibration.
+(3) The K/V-free folded attention at C = 512 (`attn_fold_kernel<512>`) against the oracle's explicit
+    qkv conv + as-executed local attention + proj on random (non-constant) data.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+import teacher_cases as tc
+
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_c3.pt")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(PATH), reason="golden_c3.pt not generated")
+def test_two_trainer_steps_at_c3_shapes_match_the_reference_trainer(cuda_dev, tmp_path):
+    from lunaris_orion_b200.train_hybrid import TrainingManager, build_arg_parser
+    gold = torch.load(PATH, weights_only=False)
+    cfg = gold["cfg"]
+    args = build_arg_parser().parse_args([
+        "--data_dir", "synthetic", "--output_dir", str(tmp_path), "--batch_size", str(cfg["B"]),
+        "--gradient_accumulation_steps", "1", "--latent_dim", str(cfg["latent"]), "--embedding_dim", str(cfg["emb"]),
+        "--feature_dim", str(cfg["feat"]), "--seed", str(cfg["seed"]), "--vae_lr", str(cfg["vae_lr"]),
+        "--teacher_lr", str(cfg["teacher_lr"])])
+    tm = TrainingManager(args, device=cuda_dev)
+    for m in tm.teacher.modules():
+        if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout2d)):
+            m.p = 0.0
+    outs = []
+    hook = tm.teacher.register_forward_hook(lambda mod, inp, o: outs.append(
+        {k: o[k].detach().float().cpu() for k in ("quality_scores", "semantic_score", "expert_weights")}))
+    x = tc.images(cfg["B"], cfg["img_seed"]).to(cuda_dev)
+    torch.manual_seed(cfg["eps_seed"])
+    m0 = tm._process_batch(x, 0)
+    ref0 = gold["steps"][0]
+    pass_b = outs[1]
+    report = {"step0": {k: (m0[k], ref0["metrics"][k]) for k in ref0["metrics"]}}
+
+    for k in ("recon_loss", "kl_loss", "vae_loss"):
+        assert abs(m0[k] - ref0["metrics"][k]) <= 0.03 * abs(ref0["metrics"][k]) + 1e-4, (k, m0[k], ref0["metrics"][k])
+    assert abs(m0["advantage"]) < 1e-6 and abs(m0["pg_loss"]) < 1e-6
+    # heads: sigmoid / softmax outputs of ill-conditioned MLPs (SURVEY.md 7 hard part 6) compared as logits per sample
+    dq = (tc.logit_c(pass_b["quality_scores"]) - tc.logit_c(ref0["pass_b"]["quality_scores"])).abs().max().item()
+    dsem = (tc.logit_c(pass_b["semantic_score"]) - tc.logit_c(ref0["pass_b"]["semantic_score"])).abs().max().item()
+    dw = (pass_b["expert_weights"] - ref0["pass_b"]["expert_weights"]).abs().max().item()
+    q_scale = tc.logit_c(ref0["pass_b"]["quality_scores"]).abs().max().item()
+    s_scale = tc.logit_c(ref0["pass_b"]["semantic_score"]).abs().max().item()
+    report["heads_step0"] = {"quality_logit_abs": dq, "quality_logit_scale": q_scale, "semantic_logit_abs": dsem,
+                             "semantic_logit_scale": s_scale, "expert_weights_abs": dw}
+    rfp = tc.fingerprint_k(tm._last_recon, cfg["samples"])
+    report["recon_samples_rel"] = float((rfp["samples"] - ref0["recon_fp"]["samples"]).abs().max() /
+                                        ref0["recon_fp"]["samples"].abs().max())
+
+    none = sorted(n for n, p in tm.teacher.named_parameters() if p.grad is None)
+    assert none == ref0["teacher_none"]
+    sd = tm.teacher.state_dict()
+    for k, v in ref0["teacher_nbt"].items():
+        assert int(sd[k]) == v, k
+    assert abs(tm.vae_optimizer.param_groups[0]["lr"] - ref0["vae_lr"]) < 1e-12
+    assert abs(tm.teacher_optimizer.param_groups[0]["lr"] - ref0["teacher_lr"]) < 1e-12
+
+    # gradients as clip_grad_norm_ left them: aggregate L1 + value / sign agreement on 64 samples per tensor
+    agree = {}
+    for name, model, key in (("vae", tm.vae, "vae_grads"), ("teacher", tm.teacher, "teacher_grads")):
+        num = den = 0.0
+        for n, p in model.named_parameters():
+            if p.grad is None:
+                continue
+            r, o = ref0[key][n], tc.fingerprint(p.grad)
+            num += abs(o["abs"] - r["abs"])
+            den += r["abs"]
+        agree[name] = tc.sample_agreement(((n, p.grad) for n, p in model.named_parameters() if p.grad is not None),
+                                          ref0[key])
+        agree[name]["aggregate_l1"] = num / den
+    report["grads"] = agree
+    # updated parameters: Adam's first step moves every element by lr * sign(g); a sample further than one lr from the
+    # reference's updated value took the step in the opposite direction
+    flips = {}
+    for name, model, key, lr in (("vae", tm.vae, "vae_params_after", cfg["vae_lr"]),
+                                 ("teacher", tm.teacher, "teacher_params_after", cfg["teacher_lr"])):
+        bad = tot = 0
+        for n, p in model.named_parameters():
+            if n not in ref0[key] or n.endswith("shortcut.0.bias"):
+                continue
+            d = (tc.fingerprint_k(p, cfg["samples"])["samples"] - ref0[key][n]["samples"]).abs()
+            bad += int((d > 1.0 * lr).sum())
+            tot += d.numel()
+        flips[name] = bad / tot
+    report["param_samples_stepped_in_opposite_direction"] = flips
+
+    outs.clear()
+    m1 = tm._process_batch(x, 1)
+    ref1 = gold["steps"][1]
+    report["step1"] = {k: (m1[k], ref1["metrics"][k]) for k in ref1["metrics"]}
+    hook.remove()
+    if os.path.isdir(OUT):
+        json.dump(report, open(os.path.join(OUT, "c3_parity_report.json"), "w"), indent=1, default=str)
+
+    assert dq <= 0.05 * q_scale + 0.05, report["heads_step0"]
+    assert dsem <= 0.05 * s_scale + 0.05, report["heads_step0"]
+    assert dw <= 0.02, report["heads_step0"]
+    assert report["recon_samples_rel"] < 0.05
+    assert agree["vae"]["aggregate_l1"] < 0.05 and agree["teacher"]["aggregate_l1"] < 0.10, agree
+    for name in ("vae", "teacher"):
+        assert agree[name]["cosine"] > 0.99, agree
+        assert agree[name]["sign_agree"] > 0.98, agree
+        assert agree[name]["value_within_10pct"] > 0.95, agree
+        assert flips[name] < 0.03, flips
+    # second step runs on the UPDATED weights (lr 3e-4 / 2e-4: the reference's KL jumps to 13.1 after one update)
+    for k in ("recon_loss", "vae_loss"):
+        assert abs(m1[k] - ref1["metrics"][k]) <= 0.05 * abs(ref1["metrics"][k]) + 1e-4, (k, m1[k], ref1["metrics"][k])
+    assert abs(m1["kl_loss"] - ref1["metrics"]["kl_loss"]) <= 0.10 * abs(ref1["metrics"]["kl_loss"]) + 1e-3
+    assert abs(m1["quality_scores"] - ref1["metrics"]["quality_scores"]) <= 0.10
+    assert abs(tm.vae_optimizer.param_groups[0]["lr"] - ref1["vae_lr"]) < 1e-12
+    sd = tm.teacher.state_dict()
+    for k, v in ref1["teacher_nbt"].items():
+        assert int(sd[k]) == v, k
+
+
+@pytest.mark.gpu
+def test_teacher_trunk_feat512_forward_backward_within_bf16_calibration(cuda_dev):
+    """feat 512 / head_dim 64: pooled expert outputs and all 100 live gradient tensors elementwise vs the oracle."""
+    rep = tc.trunk_report(cuda_dev, B=2, feat=512, calibrate=True)
+    if os.path.isdir(OUT):
+        json.dump(rep, open(os.path.join(OUT, "c3_trunk_report.json"), "w"), indent=1, default=str)
+    assert rep["grad_keys_equal"]
+    assert rep["fe_pool"] < 1e-2
+    assert rep["pool"] <= 3 * rep["cal_pool"] + 2e-3, rep
+    assert rep["grad_rel_max"] <= 3 * rep["cal_grad_rel_max"] + 0.02, rep["grad_worst"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw", [64, 128])
+def test_folded_attention_c512_matches_oracle(cuda_dev, hw):
+    """PixelArtAttention(512) forward (attn_fold_kernel<512>, head_dim 64) on random data vs the oracle's explicit
+    qkv conv + as-executed local attention + proj (lunar_evaluator.py:146-227), eval mode; 2 % of max |ref|."""
+    import torch.nn.functional as F
+    from lunaris_orion_b200 import lunar_evaluator as le
+    from oracle import restatement as R
+    torch.manual_seed(14)
+    att = le.PixelArtAttention(512, dropout=0.0).to(cuda_dev).eval()
+    with torch.no_grad():
+        att.qkv.bias.normal_(0, 0.2)
+        att.proj.bias.normal_(0, 0.2)
+    x = torch.randn(2, 512, hw, hw, generator=torch.Generator().manual_seed(15))
+    with torch.no_grad():
+        mine = att(x.to(cuda_dev)).cpu()
+        w = {k: v.detach().cpu().float() for k, v in att.state_dict().items() if v is not None}
+        qkv = F.conv2d(x, w["qkv.weight"], w["qkv.bias"])
+        ref = F.conv2d(R.local_attention(qkv, "reference"), w["proj.weight"], w["proj.bias"])
+    nq = hw * hw // 32 + 31
+    flat, rflat = mine.permute(0, 2, 3, 1).reshape(2, -1, 512), ref.permute(0, 2, 3, 1).reshape(2, -1, 512)
+    assert tc.rel_err(flat[:, :nq], rflat[:, :nq]) < 2e-2
+    assert torch.allclose(flat[:, nq:], w["proj.bias"].to(torch.bfloat16).float().expand_as(flat[:, nq:]))
