@@ -254,15 +254,17 @@ int lun_flash_attn2d_dqk_bf16(const void* qk, const void* v, const void* dy, con
 int lun_pack_weight_bf16(const float* src, void* dst, int A, int B, int T, int transpose, void* stream);
 
 /* Optimizer boundary (train_hybrid.py:906-922): clip_grad_norm_(max_norm) + AdamW over all tensors of one model in two
- * multi-tensor launches. table: device array of {float* param, grad, exp_avg, exp_avg_sq; long long numel} (40 bytes
- * each); chunks: device array of int2 {tensor index, chunk index} with 8192 elements per chunk; norm2: device float[1024]
- * of per-block partial sums of g^2, summed in a fixed order by the update kernel (no host sync, bitwise reproducible). bias_c1 = 1 - beta1^t,
- * bias_c2_sqrt = sqrt(1 - beta2^t). Semantics = torch.optim.AdamW (decoupled decay, eps outside the bias-corrected
- * sqrt) on the gradients scaled in place by min(1, max_norm / (norm + 1e-6)). */
-int lun_multi_grad_sumsq(const void* table, const void* chunks, int nchunks, float* norm2, void* stream);
+ * multi-tensor launches. table: device array of 72-byte rows {float* param, grad, exp_avg, exp_avg_sq; long long numel;
+ * float lr, beta1, beta2, eps, weight_decay, bias_c1 = 1 - beta1^t, bias_c2_sqrt = sqrt(1 - beta2^t), pad} - hyper-
+ * parameters and step count per tensor (param groups, late first gradients); chunks: device array of int2 {tensor index,
+ * chunk index} with 8192 elements per chunk; norm2: device float[1024] of per-block partial sums of (g * grad_scale)^2,
+ * summed in a fixed order by the update kernel (no host sync, bitwise reproducible). grad_scale folds the data-parallel
+ * 1/world average into the pass. Semantics = torch.optim.AdamW (decoupled decay, eps outside the bias-corrected sqrt) on
+ * the gradients scaled in place by grad_scale * min(1, max_norm / (norm + 1e-6)). */
+int lun_multi_grad_sumsq(const void* table, const void* chunks, int nchunks, float grad_scale, float* norm2,
+                         void* stream);
 int lun_multi_clip_adamw(const void* table, const void* chunks, int nchunks, const float* norm2, float max_norm,
-                         float lr, float beta1, float beta2, float eps, float weight_decay, float bias_c1,
-                         float bias_c2_sqrt, void* stream);
+                         float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

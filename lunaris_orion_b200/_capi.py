@@ -109,9 +109,8 @@ SIGNATURES = {
     "lun_flash_attn2d_dqk_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_void_p],
     "lun_pack_weight_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    "lun_multi_grad_sumsq": [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
-    "lun_multi_clip_adamw": [c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
-                             c_float, c_float, c_void_p],
+    "lun_multi_grad_sumsq": [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p],
+    "lun_multi_clip_adamw": [c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_void_p],
     "lun_fe_branches": [c_void_p, c_void_p, c_void_p, c_pp, c_pp, c_pp, c_pp, c_void_p, c_int, c_int, c_int, c_float,
                         c_void_p],
 }

@@ -1,9 +1,12 @@
 // Optimizer boundary of the step (train_hybrid.py:906-922): clip_grad_norm_ + AdamW as two multi-tensor kernels.
-//   kernel 1: sum of squares of every gradient tensor of one model -> norm2[0]            (one pass over the grads)
+//   kernel 1: sum of squares of every gradient tensor of one model -> norm2[]             (one pass over the grads)
 //   kernel 2: coef = min(1, max_norm / (sqrt(norm2) + 1e-6)); g *= coef (the reference's in-place clip);
 //             decoupled weight decay + Adam moments + parameter update (torch.optim.AdamW semantics, fp32)
-// The tensors are described by a device table of {param, grad, exp_avg, exp_avg_sq, numel}; work is cut into fixed
-// chunks so one launch covers all ~100 tensors of a model. State layout stays torch's (checkpoint contract).
+// Both read the gradient as g * grad_scale: data-parallel ranks all-reduce SUMS and fold the 1/world average in here.
+// The tensors are described by a device table of {param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps,
+// weight_decay, 1 - beta1^t, sqrt(1 - beta2^t)}: hyper-parameters and the step count are PER TENSOR, so several param
+// groups and parameters whose first gradient arrives late update exactly like torch.optim.AdamW. Work is cut into
+// fixed chunks so one launch covers all ~100 tensors of a model. State layout stays torch's (checkpoint contract).
 #include "../../include/lunaris_b200.h"
 #include "elem_common.cuh"
 #include "launch_count.cuh"
@@ -16,18 +19,21 @@ struct OptTensor {
   float* m;
   float* v;
   long long n;
+  float lr, beta1, beta2, eps, wd, bias_c1, bias_c2_sqrt, pad;
 };
+static_assert(sizeof(OptTensor) == 72, "host table rows are 72 bytes (lunaris_orion_b200/optim.py)");
 constexpr int kOptChunk = 8192;   // elements per block-iteration
 
 __global__ void __launch_bounds__(256) multi_sumsq_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ chunks,
-                                                          int nchunks, float* __restrict__ norm2) {
+                                                          int nchunks, float grad_scale,
+                                                          float* __restrict__ norm2) {
   float acc = 0.f;
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const OptTensor t = tab[chunks[c].x];
     const long long base = (long long)chunks[c].y * kOptChunk;
     const long long end = base + kOptChunk < t.n ? base + kOptChunk : t.n;
     for (long long i = base + threadIdx.x; i < end; i += 256) {
-      const float g = t.g[i];
+      const float g = t.g[i] * grad_scale;
       acc += g * g;
     }
   }
@@ -44,8 +50,7 @@ __global__ void __launch_bounds__(256) multi_sumsq_kernel(const OptTensor* __res
 
 __global__ void __launch_bounds__(256) multi_adamw_kernel(const OptTensor* __restrict__ tab, const int2* __restrict__ chunks,
                                                           int nchunks, const float* __restrict__ norm2, int npart,
-                                                          float max_norm, float lr, float beta1, float beta2,
-                                                          float eps, float wd, float bias_c1, float bias_c2_sqrt) {
+                                                          float max_norm, float grad_scale) {
   __shared__ float s_norm2;
   if (threadIdx.x == 0) {
     float tot = 0.f;
@@ -55,14 +60,15 @@ __global__ void __launch_bounds__(256) multi_adamw_kernel(const OptTensor* __res
   __syncthreads();
   const float norm = sqrtf(s_norm2);
   const float coef = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
-  const float step_size = lr / bias_c1;
-  const float decay = 1.f - lr * wd;
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const OptTensor t = tab[chunks[c].x];
+    const float step_size = t.lr / t.bias_c1;
+    const float decay = 1.f - t.lr * t.wd;
+    const float beta1 = t.beta1, beta2 = t.beta2, eps = t.eps, bias_c2_sqrt = t.bias_c2_sqrt;
     const long long base = (long long)chunks[c].y * kOptChunk;
     const long long end = base + kOptChunk < t.n ? base + kOptChunk : t.n;
     for (long long i = base + threadIdx.x; i < end; i += 256) {
-      const float g = t.g[i] * coef;
+      const float g = t.g[i] * grad_scale * coef;
       t.g[i] = g;
       const float m = beta1 * t.m[i] + (1.f - beta1) * g;
       const float v = beta2 * t.v[i] + (1.f - beta2) * g * g;
@@ -96,24 +102,23 @@ using namespace lun;
 
 extern "C" {
 
-int lun_multi_grad_sumsq(const void* table, const void* chunks, int nchunks, float* norm2, void* stream) {
+int lun_multi_grad_sumsq(const void* table, const void* chunks, int nchunks, float grad_scale, float* norm2,
+                         void* stream) {
   if (nchunks <= 0) return LUN_OK;
   int grid = nchunks < 1024 ? nchunks : 1024;      // == number of partial sums written to norm2[]
   multi_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const OptTensor*)table, (const int2*)chunks, nchunks,
-                                                            norm2);
+                                                            grad_scale, norm2);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }
 
 int lun_multi_clip_adamw(const void* table, const void* chunks, int nchunks, const float* norm2, float max_norm,
-                         float lr, float beta1, float beta2, float eps, float weight_decay, float bias_c1,
-                         float bias_c2_sqrt, void* stream) {
+                         float grad_scale, void* stream) {
   if (nchunks <= 0) return LUN_OK;
   int grid = nchunks < 148 * 8 ? nchunks : 148 * 8;
   const int npart = nchunks < 1024 ? nchunks : 1024;
   multi_adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const OptTensor*)table, (const int2*)chunks, nchunks,
-                                                            norm2, npart, max_norm, lr, beta1, beta2, eps,
-                                                            weight_decay, bias_c1, bias_c2_sqrt);
+                                                            norm2, npart, max_norm, grad_scale);
   lun::note_launch(1);
   return cudaGetLastError() == cudaSuccess ? LUN_OK : LUN_E_LAUNCH;
 }

@@ -11,14 +11,17 @@ the reference's python float), so a step has a single device->host copy: the pac
 import argparse
 import os
 import time
+import warnings
 
 import numpy as np
 import torch
 import torch.distributed as dist
 from torch.optim.lr_scheduler import CosineAnnealingWarmRestarts
 
+from ._capi import LunarisB200Error
+from .data import PixelArtDataset, SpriteLoader, SyntheticSprites, split_indices
 from .lunar_evaluator import LunarMoETeacher
-from .lunar_generate import LunarisCoreVAE, sprites_to_tensor, vae_losses
+from .lunar_generate import LunarisCoreVAE, vae_losses
 from .optim import ClipAdamW
 
 METRIC_KEYS = ("recon_loss", "kl_loss", "quality_loss", "pg_loss", "semantic_reward", "quality_reward", "baseline",
@@ -68,12 +71,16 @@ def build_arg_parser():
 
 # ====================================================================================================== data parallel
 class GradBucketReducer:
-    """Bucketed gradient all-reduce (average) launched from grad-ready hooks on a side stream.
+    """Bucketed gradient all-reduce launched from grad-ready hooks on a side stream (the reference has no data
+    parallelism; SURVEY.md 8e defines it: batch-sharded ranks, one gradient average per optimizer step).
 
-    Parameters are packed into ~bucket_mb buckets in the given order; a bucket is flattened and all-reduced as soon as
-    every member has its gradient, so the VAE's buckets travel over NVLink while the Teacher backward still runs.
-    Parameters that never get a gradient (the reference's None-set) are simply never waited for: finish() reduces
-    whatever is ready, identically on every rank."""
+    `params` is the STATIC live set in the order gradients become ready (for the hybrid step: every VAE tensor, then
+    the Teacher tensors of the reference's executed gradient set). They are packed into ~bucket_mb buckets, each with a
+    persistent flat fp32 buffer. When the last member of a bucket gets its gradient, one multi-tensor copy moves the
+    members' gradients into the flat buffer, `p.grad` is re-pointed at its slice (so the optimizer reads the reduced
+    values in place: no concatenation, no write-back copies), and the bucket's all-reduce (SUM) starts on the side
+    stream, overlapping the rest of the backward. The 1/world average is folded into the optimizer
+    (`ClipAdamW.grad_scale`); `finish(average=True)` scales here instead for callers without it."""
 
     def __init__(self, params, group=None, bucket_mb=32):
         self.group = group
@@ -89,9 +96,19 @@ class GradBucketReducer:
         if cur:
             self.buckets.append(cur)
         self.bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self.flat, self.views = [], {}
+        for b in self.buckets:
+            flat = torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device)
+            off = 0
+            for p in b:
+                self.views[id(p)] = flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            self.flat.append(flat)
         self.ready = [0] * len(self.buckets)
         self.inflight = {}
         self.enabled = True
+        self.keep_local = False            # dp_check: keep a copy of every bucket's local gradients
+        self.local = {}
         self.cuda = bool(self.params) and self.params[0].is_cuda
         self.stream = torch.cuda.Stream() if self.cuda else None
         self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] \
@@ -106,87 +123,110 @@ class GradBucketReducer:
             self._launch(i)
 
     def _launch(self, i):
-        members = [p for p in self.buckets[i] if p.grad is not None]
-        if not members or i in self.inflight:
+        if i in self.inflight:
             return
+        have = [p for p in self.buckets[i] if p.grad is not None]
+        if not have:
+            return
+        flat = self.flat[i]
+        if len(have) < len(self.buckets[i]):
+            flat.zero_()                   # members without a gradient on this rank contribute zeros
+        torch._foreach_copy_([self.views[id(p)] for p in have], [p.grad for p in have])
+        for p in have:
+            p.grad = self.views[id(p)]
+        if self.keep_local:
+            self.local[i] = flat.clone()
         if self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                flat = torch.cat([p.grad.reshape(-1).float() for p in members])
                 work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         else:
-            flat = torch.cat([p.grad.reshape(-1).float() for p in members])
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self.inflight[i] = (members, flat, work)
+        self.inflight[i] = work
 
-    def finish(self):
-        """Reduce any bucket that did not fill (None-set members), wait, and write the averaged grads back."""
+    def finish(self, average=False):
+        """Start whatever did not fire from a hook, wait for every bucket. After this `p.grad` of every live parameter
+        is a view of the summed (average=True: averaged) gradients."""
         if self.world == 1:
             return
         for i in range(len(self.buckets)):
             self._launch(i)
-        for i, (members, flat, work) in sorted(self.inflight.items()):
+        for i, work in sorted(self.inflight.items()):
             work.wait()
-            if self.cuda:
-                torch.cuda.current_stream().wait_stream(self.stream)
-            off = 0
-            flat.mul_(1.0 / self.world)
-            for p in members:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+        if self.cuda and self.inflight:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        if average:
+            for i in self.inflight:
+                self.flat[i].mul_(1.0 / self.world)
         self.inflight.clear()
         self.ready = [0] * len(self.buckets)
 
 
-# ====================================================================================================== data
-class SpriteData:
-    """sprites*.npy (uint8 [N,128,128,3]) reader compatible with the reference's PixelArtDataset normalisation
-    (train_hybrid.py:181-182: x/127.5 - 1, HWC -> CHW), sharded by rank; 'synthetic' generates SURVEY.md §8d data."""
+def live_parameters(vae, teacher):
+    """The tensors that receive gradients in the hybrid step, in the order they become ready: all 72 VAE tensors
+    (vae_loss.backward()), then - from teacher_loss.backward() - the gate and quality heads and the trunk tensors of
+    the reference's executed gradient set."""
+    from .lunar_evaluator import _trunk_grad_params
+    heads = list(teacher.gate.parameters()) + list(teacher.quality_heads.parameters())
+    return list(vae.parameters()) + heads + _trunk_grad_params(teacher)
 
-    def __init__(self, data_dir, batch_size, rank=0, world=1, seed=1234):
-        if data_dir == "synthetic":
-            rng = np.random.default_rng(seed + rank)
-            self.arr = rng.integers(0, 256, (max(4 * batch_size, 64), 128, 128, 3), dtype=np.uint8)
+
+class EarlyStopping:
+    """Patience counter on the epoch loss (train_hybrid.py:206-225)."""
+
+    def __init__(self, patience=7, min_delta=0.0):
+        self.patience, self.min_delta = patience, min_delta
+        self.counter, self.best_loss, self.early_stop = 0, None, False
+
+    def __call__(self, loss):
+        if self.best_loss is None:
+            self.best_loss = loss
+        elif loss > self.best_loss + self.min_delta:
+            self.counter += 1
+            if self.counter >= self.patience:
+                self.early_stop = True
         else:
-            files = sorted(f for f in os.listdir(data_dir) if f.startswith("sprites") and f.endswith(".npy"))
-            if not files:
-                raise FileNotFoundError(f"no sprites*.npy under {data_dir}")
-            arrs = [np.load(os.path.join(data_dir, f), mmap_mode="r") for f in files]
-            self.arr = arrs[0] if len(arrs) == 1 else np.concatenate(arrs)
-        self.bs, self.rank, self.world = batch_size, rank, world
+            self.best_loss = loss
+            self.counter = 0
 
-    def __len__(self):
-        return len(self.arr) // (self.bs * self.world)
 
-    def batches(self, epoch, device):
-        n = len(self)
-        order = np.random.default_rng(epoch).permutation(len(self.arr))[: n * self.bs * self.world]
-        order = order.reshape(n, self.world, self.bs)[:, self.rank]
-        for idx in order:
-            u8 = torch.from_numpy(np.ascontiguousarray(self.arr[np.sort(idx)]))
-            if device.type == "cuda":
-                yield sprites_to_tensor(u8.pin_memory().to(device, non_blocking=True))
-            else:
-                yield u8.permute(0, 3, 1, 2).float().div_(127.5).sub_(1.0)
+# flags of the reference CLI that this trainer parses (same surface) but that cannot change its behaviour
+_INERT_FLAGS = {
+    "mixed_precision": "the B200 path always computes in bf16 with fp32 accumulation (the reference's switch selects "
+                       "fp16 autocast + GradScaler)",
+    "compile": "the step already runs hand-written kernels; there is nothing for torch.compile to do",
+    "memory_efficient": "parsed and ignored by the reference too (train_hybrid.py:1132)",
+    "num_workers": "batches are gathered by one prefetch thread, not by DataLoader worker processes",
+    "chunk_size": "parsed and ignored by the reference too; the attention chunk is fixed at 32 (lunar_evaluator.py:148)",
+    "save_every": "parsed and ignored by the reference too", "sample_every": "parsed and ignored by the reference too",
+    "keep_n_checkpoints": "parsed and ignored by the reference too",
+    "eval_save_freq": "the PNG eval-sample dump (train_hybrid.py:718-789) is outside the accelerated path",
+}
 
 
 # ====================================================================================================== trainer
 class TrainingManager:
-    """Drop-in for the reference's TrainingManager on the hot path: models, optimizers, schedulers, one step,
-    checkpoint save / load (train_hybrid.py:382-404, 502-527, 594-615, 791-836, 838-954)."""
+    """Drop-in for the reference's TrainingManager on the hot path: models, optimizers, schedulers, data, one step,
+    checkpoint save / load (train_hybrid.py:382-404, 502-585, 594-615, 791-836, 838-954)."""
 
     def __init__(self, args, device=None):
         self.args = args
         self.rank = int(os.environ.get("RANK", 0))
         self.world = int(os.environ.get("WORLD_SIZE", 1))
         self.local_rank = int(os.environ.get("LOCAL_RANK", 0))
+        if getattr(args, "force_cpu", False):
+            raise LunarisB200Error("--force_cpu: lunaris_orion_b200 has no CPU path (use the reference trainer on CPU)")
         if device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("lunaris_orion_b200 needs a CUDA device (B200, sm_100a): there is no CPU path")
             device = torch.device("cuda", self.local_rank)
             torch.cuda.set_device(device)
         self.device = device
+        if self.rank == 0:
+            defaults = build_arg_parser().parse_args(["--data_dir", "x"])
+            for flag, why in _INERT_FLAGS.items():
+                if getattr(args, flag, None) != getattr(defaults, flag):
+                    warnings.warn(f"--{flag} has no effect in lunaris_orion_b200: {why}", stacklevel=2)
         if self.world > 1 and not dist.is_initialized():
             dist.init_process_group("nccl", device_id=device)
         # identical initial weights on every rank: seed before construction, VAE first (train_hybrid.py:1138, 394, 400)
@@ -196,9 +236,6 @@ class TrainingManager:
         self.vae = LunarisCoreVAE(latent_dim=args.latent_dim).to(device).train()
         self.teacher = LunarMoETeacher(num_experts=args.num_experts, feature_dim=args.feature_dim,
                                        embedding_dim=args.embedding_dim).to(device).train()
-        # per-rank dropout / epsilon streams
-        torch.manual_seed(args.seed + self.rank)
-        torch.cuda.manual_seed_all(args.seed + self.rank)
         # clip_grad_norm_ + AdamW fused into two multi-tensor launches per model (state layout == torch.optim.AdamW)
         mk = dict(weight_decay=args.weight_decay, betas=(0.9, 0.999), max_grad_norm=args.max_grad_norm)
         self.vae_optimizer = ClipAdamW(self.vae.parameters(), lr=args.vae_lr, **mk)
@@ -206,9 +243,20 @@ class TrainingManager:
         sk = dict(T_0=args.scheduler_t0, T_mult=2, eta_min=args.min_lr)
         self.vae_scheduler = CosineAnnealingWarmRestarts(self.vae_optimizer, **sk)
         self.teacher_scheduler = CosineAnnealingWarmRestarts(self.teacher_optimizer, **sk)
-        self.reducer = GradBucketReducer(list(self.vae.parameters()) + list(self.teacher.parameters())) \
-            if self.world > 1 else None
-        self.baseline = None          # device scalar (reference: python float, train_hybrid.py:875-879)
+        # data after the models, like the reference (train_hybrid.py:273-275): the 90/10 split continues the seeded
+        # CPU stream right after the weight init, so one process sees the reference's split (and first-epoch order)
+        self._setup_data()
+        # per-rank dropout / epsilon streams (rank 0 keeps the reference's stream position)
+        if self.rank > 0:
+            torch.manual_seed(args.seed + self.rank)
+        torch.cuda.manual_seed_all(args.seed + self.rank)
+        self.reducer = None
+        if self.world > 1:
+            self.reducer = GradBucketReducer(live_parameters(self.vae, self.teacher))
+            self.vae_optimizer.grad_scale = self.teacher_optimizer.grad_scale = 1.0 / self.world
+        self._after_reduce = None     # bench.py dp_check: called between the gradient all-reduce and the optimizer
+        self.baseline = None          # float64 device scalar (reference: python float, train_hybrid.py:875-879)
+        self.early_stopping = EarlyStopping(patience=args.early_stopping_patience)
         self.global_step = 0
         self.best_loss = float("inf")
         self.reward_scale = args.reward_scale
@@ -217,6 +265,22 @@ class TrainingManager:
         self.checkpoint_dir = os.path.join(args.output_dir, "checkpoints")
         if getattr(args, "resume_from", None):
             self._load_checkpoint(args.resume_from)
+
+    # ------------------------------------------------------------------ data (train_hybrid.py:529-585)
+    def _setup_data(self):
+        a = self.args
+        if a.data_dir == "synthetic":
+            self.dataset = SyntheticSprites(max(8 * a.batch_size * self.world, 64))
+        else:
+            self.dataset = PixelArtDataset(a.data_dir)
+        train_idx, val_idx = split_indices(len(self.dataset))            # consumes the default generator (:555)
+        gen = None
+        if self.world > 1:                # every rank must draw the same epoch permutations: a shared private stream
+            gen = torch.Generator()
+            gen.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+        mk = dict(batch_size=a.batch_size, device=self.device, rank=self.rank, world=self.world)
+        self.train_loader = SpriteLoader(self.dataset, train_idx, shuffle=True, generator=gen, **mk)
+        self.val_loader = SpriteLoader(self.dataset, val_idx, shuffle=False, **mk)
 
     # ------------------------------------------------------------------ one step (train_hybrid.py:838-954)
     def _process_batch(self, images, batch_idx, return_tensor=False):
@@ -235,12 +299,12 @@ class TrainingManager:
         semantic_score = teacher_eval['semantic_score']
         quality_reward = quality_scores.mean(dim=1, keepdim=True)
         total_reward = quality_reward + self.semantic_weight * semantic_score
-        tr = total_reward.mean().detach()
+        tr = total_reward.mean().detach().double()                      # the reference's EMA is a python float (f64)
         if self.baseline is None:
             self.baseline = tr
         else:
             self.baseline = self.baseline_momentum * self.baseline + (1 - self.baseline_momentum) * tr
-        advantage = (total_reward - self.baseline).detach() * self.reward_scale
+        advantage = (total_reward - self.baseline.float()).detach() * self.reward_scale
         pg_loss = -(advantage * recon_loss).mean()
         vae_loss = (a.recon_weight * recon_loss + a.kl_weight * kl_loss + pg_loss) / accum
         quality_loss = -torch.mean(quality_scores)
@@ -255,13 +319,15 @@ class TrainingManager:
         if boundary:
             if self.reducer is not None:
                 self.reducer.finish()
+                if self._after_reduce is not None:
+                    self._after_reduce(self)
             self.vae_optimizer.step()                    # clip (train_hybrid.py:913-915) happens inside the fused step
             self.teacher_optimizer.step()
             self.vae_scheduler.step()
             self.teacher_scheduler.step()
 
         packed = torch.stack([recon_loss, kl_loss, quality_loss, pg_loss, semantic_score.mean(), quality_reward.mean(),
-                              self.baseline, advantage.mean(), vae_loss, teacher_loss, vae_loss + teacher_loss,
+                              self.baseline.float(), advantage.mean(), vae_loss, teacher_loss, vae_loss + teacher_loss,
                               quality_scores.mean()]).detach().float()
         self.global_step += 1
         self._last_recon = recon.detach()
@@ -304,11 +370,13 @@ class TrainingManager:
 
     # ------------------------------------------------------------------ loop (train_hybrid.py:956-1070, hot part only)
     def train(self):
+        """Epoch loop. Deviation from the reference, on purpose: the reference never appends to `epoch_losses`
+        (train_hybrid.py:987), so its epoch mean is NaN, `best.pt` is never written and early stopping never fires
+        (SURVEY.md 0.8); here the epoch mean of `total_loss` drives both, as the code evidently intends."""
         a = self.args
-        data = SpriteData(a.data_dir, a.batch_size, self.rank, self.world)
         for epoch in range(a.num_epochs):
             t0, losses = time.time(), []
-            for batch_idx, images in enumerate(data.batches(epoch, self.device)):
+            for batch_idx, images in enumerate(self.train_loader.epoch()):
                 m = self._process_batch(images, batch_idx)
                 losses.append(m['total_loss'])
                 if self.rank == 0 and self.global_step % a.log_every == 0:
@@ -318,6 +386,11 @@ class TrainingManager:
                 n_img = len(losses) * a.batch_size * self.world
                 print(f"epoch {epoch} loss {epoch_loss:.4f} {n_img / max(time.time() - t0, 1e-9):.1f} img/s",
                       flush=True)
+            self.early_stopping(epoch_loss)
+            if self.early_stopping.early_stop:
+                if self.rank == 0:
+                    print("Early stopping triggered", flush=True)
+                break
             if epoch_loss < self.best_loss:
                 self.best_loss = epoch_loss
                 self._save_checkpoint(is_best=True)

@@ -26,8 +26,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import reference_loader  # noqa: E402
 from oracle.make_golden import images  # noqa: E402
+from oracle.ref_harness import drive_reference_trainer, write_sprites  # noqa: E402
 
 CFG = dict(feat=512, emb=256, latent=512, B=4, seed=42, img_seed=17, eps_seed=231, vae_lr=3e-4, teacher_lr=2e-4,
            steps=2, samples=64)
@@ -38,42 +38,6 @@ def fingerprint(t, k=64):
     t = t.detach().double().flatten()
     idx = torch.linspace(0, t.numel() - 1, min(k, t.numel())).long()
     return {"sum": t.sum().item(), "abs": t.abs().sum().item(), "n": t.numel(), "samples": t[idx].float().clone()}
-
-
-def drive_reference_trainer(cfg, data_dir, out_dir, extra=()):
-    """build the unmodified reference TrainingManager through its own main()."""
-    reference_loader.load()
-    if reference_loader.REF not in sys.path:
-        sys.path.insert(0, reference_loader.REF)
-    import train_hybrid as th
-    if not getattr(th, "_lun_dl_shim", False):
-        _DL = th.DataLoader
-        th.DataLoader = lambda ds, **kw: _DL(ds, **{**kw, "timeout": 0 if kw.get("num_workers", 0) == 0
-                                                      else kw.get("timeout", 0)})
-        th._lun_dl_shim = True
-    cap = {}
-    th.TrainingManager.train = lambda self: cap.__setitem__("tm", self)
-    argv = sys.argv
-    sys.argv = ["train_hybrid.py", "--data_dir", data_dir, "--output_dir", out_dir, "--force_cpu",
-                "--batch_size", str(cfg["B"]), "--gradient_accumulation_steps", str(cfg.get("accum", 1)),
-                "--num_workers", "0", "--latent_dim", str(cfg["latent"]), "--embedding_dim", str(cfg["emb"]),
-                "--feature_dim", str(cfg["feat"]), "--seed", str(cfg["seed"]),
-                "--vae_lr", str(cfg.get("vae_lr", 1e-4)), "--teacher_lr", str(cfg.get("teacher_lr", 1e-4))] + list(extra)
-    try:
-        th.main()
-    finally:
-        sys.argv = argv
-    return cap["tm"]
-
-
-def write_sprites(data, n):
-    os.makedirs(data, exist_ok=True)
-    np.save(os.path.join(data, "sprites_000.npy"),
-            np.random.default_rng(1234).integers(0, 256, (n, 128, 128, 3), dtype=np.uint8))
-    with open(os.path.join(data, "labels_000.csv"), "w") as f:
-        f.write("filename,category,prompt,seed,pixel_size,guidance_scale,pag_scale,num_steps\n")
-        for i in range(n):
-            f.write(f"s{i}.png,cat,prompt,{i},8,7.5,3.0,20\n")
 
 
 def main():

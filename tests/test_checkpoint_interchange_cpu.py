@@ -96,7 +96,8 @@ def test_our_trainer_loads_a_reference_checkpoint(ref_trainer, tmp_path):
             for f in ("step", "exp_avg", "exp_avg_sq"):
                 assert torch.equal(sa["state"][k][f], sb["state"][k][f]), (k, f)
         assert sa["param_groups"][0]["lr"] == sb["param_groups"][0]["lr"]
-        assert mine._t == 1                                       # bias-correction step counter restored
+        for q, st in mine.state.items():                          # bias-correction step counters restored per tensor
+            assert mine._host_step(q, st) == 1
     assert ours.vae_scheduler.state_dict()["last_epoch"] == ref_tm.vae_scheduler.state_dict()["last_epoch"]
 
 

@@ -139,6 +139,48 @@ def test_clip_adamw_matches_torch_clip_plus_adamw(cuda_dev):
 
 
 @pytest.mark.gpu
+def test_clip_adamw_param_groups_late_gradients_and_grad_scale(cuda_dev):
+    """Per-group hyper-parameters, a parameter whose first gradient arrives two steps late (its own bias-correction
+    step count, like torch's per-tensor state['step']), and grad_scale = 1/world on summed gradients == torch
+    clip + AdamW on the averaged gradients."""
+    from lunaris_orion_b200 import _capi
+    from lunaris_orion_b200.optim import ClipAdamW
+    g = torch.Generator().manual_seed(3)
+    shapes = [(40, 9), (33,), (5, 4, 3, 3)]
+    pa = [torch.randn(s, generator=g).to(cuda_dev).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+
+    def groups(ps):
+        return [dict(params=ps[:1], lr=1e-2, weight_decay=0.1, betas=(0.8, 0.99)), dict(params=ps[1:], lr=1e-3)]
+    oa = ClipAdamW(groups(pa), weight_decay=0.01, max_grad_norm=0.5)
+    oa.grad_scale = 0.25
+    ob = torch.optim.AdamW(groups(pb), weight_decay=0.01)
+    for step in range(5):
+        for i, (p, q) in enumerate(zip(pa, pb)):
+            if i == 2 and step < 2:
+                p.grad = q.grad = None                   # late first gradient
+                continue
+            gr = torch.randn(p.shape, generator=g).to(cuda_dev) * 3.0
+            p.grad, q.grad = gr.clone() * 4.0, gr.clone()             # ours holds the 4-rank SUM, torch the average
+        torch.nn.utils.clip_grad_norm_(pb, 0.5)
+        ob.step()
+        oa.step()
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=3e-5, atol=3e-6), step
+    assert float(oa.state[pa[2]]["step"]) == float(ob.state[pb[2]]["step"]) == 3.0
+    assert float(oa.state[pa[0]]["step"]) == 5.0
+    # state_dict round trip keeps the per-tensor counters (host mirror re-read from the restored state)
+    oc = ClipAdamW(groups([p.detach().clone().requires_grad_(True) for p in pa]), weight_decay=0.01, max_grad_norm=0.5)
+    oc.load_state_dict(oa.state_dict())
+    assert [oc._host_step(p, oc.state[p]) for gr_ in oc.param_groups for p in gr_["params"]] == [5, 5, 3]
+    with pytest.raises(_capi.LunarisB200Error):
+        bad = ClipAdamW([torch.zeros(3, device=cuda_dev, requires_grad=True)])
+        bad.param_groups[0]["amsgrad"] = True
+        bad.param_groups[0]["params"][0].grad = torch.ones(3, device=cuda_dev)
+        bad.step()
+
+
+@pytest.mark.gpu
 def test_forward_after_an_optimizer_step_runs_on_the_updated_weights(cuda_dev, tmp_path):
     """The kernels consume packed bf16 shadows of the fp32 parameters, cached per parameter version. After a fused
     clip + AdamW step (which writes the parameters through raw pointers) the next forward must see the NEW weights:
@@ -189,11 +231,12 @@ def test_cli_trains_an_epoch_from_sprite_files_and_resumes(cuda_dev, tmp_path):
             "--gradient_accumulation_steps", "1", "--latent_dim", "64", "--embedding_dim", "32", "--feature_dim", "64"]
     th.main(argv)
     ck = torch.load(out / "checkpoints" / "latest.pt", weights_only=True)
-    assert ck["global_step"] == 3 and (out / "checkpoints" / "best.pt").exists()          # 12 sprites / batch 4
+    # 12 sprites -> 90/10 split like the reference (train_hybrid.py:551-555): 10 training sprites, 2 full batches of 4
+    assert ck["global_step"] == 2 and (out / "checkpoints" / "best.pt").exists()
     assert all(torch.isfinite(v).all() for v in ck["vae_state_dict"].values() if v.is_floating_point())
     args = th.build_arg_parser().parse_args(argv + ["--resume_from", str(out / "checkpoints" / "latest.pt")])
     tm = th.TrainingManager(args, device=cuda_dev)
-    assert tm.global_step == 3
+    assert tm.global_step == 2
     assert abs(tm.vae_optimizer.param_groups[0]["lr"] - ck["vae_optimizer"]["param_groups"][0]["lr"]) < 1e-12
     m = tm._process_batch(tc.images(4, 2).to(cuda_dev), 0)
-    assert all(v == v for v in m.values()) and tm.global_step == 4
+    assert all(v == v for v in m.values()) and tm.global_step == 3
