@@ -3,21 +3,30 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[2] / configs[3], "C3"): batch 64 per GPU, latent 512 / emb 256 / feat 512, one
-`_process_batch` (VAE fwd, Teacher pass A + pass B, two backwards, clip, AdamW, cosine step) per step.
+Workload (BASELINE.json configs[2] / configs[3], "C3"): batch 64 per GPU, latent 512 / emb 256 / feat 512, dropout on
+(reference defaults), one `_process_batch` (VAE fwd, Teacher pass A + pass B, two backwards, clip, AdamW, cosine step)
+per step.
   value : images/s with the step's images already resident in HBM (CUDA-event timing, max over ranks)
-  e2e   : same metric through TrainingManager with HOST uint8 sprites: pinned host->device copy + normalise inside
-          the timed region and the packed 12 metrics read back every step
+  e2e   : same metric through the repo's public path: `sprites_*.npy` + `labels_*.csv` on disk -> SpriteLoader
+          (memory-mapped gather into pinned buffers, host->device copy, GPU normalise) -> TrainingManager._process_batch
+          -> the packed 12 metrics copied back and read on the host every step
   roofline : the dominant kernel (tcgen05 implicit-GEMM 3x3 conv, 512->512 at 128x128) timed alone with CUDA events;
-             algorithmic FLOPs per launch = 2 * (B*16384) * 512 * 4608
-  cpu_baseline / --impl reference : the oracle port of the reference's CPU path (oracle/restatement.py, torch fp32 on
-             all host threads) on a bounded sample of the same architecture
+             algorithmic FLOPs per launch = 2 * (B*16384) * 512 * 4608; the same shape through cuDNN beside it
+  c2 / c5  : BASELINE.json configs[1] (batch 16, accumulation 4, feat 256) and configs[4] (decoder-only sampling,
+             batch 256) measured in the same run (N=1 only)
+  dp_check : N>1 only - after the timed region one extra step verifies that the reduced gradient equals the mean of the
+             all-gathered per-rank gradients and that every rank holds bit-identical parameters
+  cpu_baseline / --impl reference : the UNMODIFIED reference trainer (oracle/_ref, byte-compiled from /root/reference by
+             oracle/make_ref.py) on the host cores: real `TrainingManager._process_batch` calls, --force_cpu semantics,
+             on a bounded batch of the same architecture
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -26,10 +35,11 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(batch=64, latent=512, emb=256, feat=512)
 GF_PER_IMG = 5443.3   # algorithmic GFLOP per image per step, as-executed, recompute excluded
+GF_PER_IMG_C2 = 1423.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (3x3 512->512, B=64, production
-# epilogue) from `ncu --set full` (profiles/r01b_ncu_conv_fprop_3x3_512_B64.txt); algorithmic bytes: 2.152e9
-NCU_TRAFFIC = {(512, 64): 1.458739e9 + 1.048327e9}
-NCU_TENSOR_PCT = {(512, 64): 95.1}     # sm__pipe_tensor_cycles_active % of elapsed, same capture (99.5 % of active)
+# epilogue) from an `ncu --set full` capture of tools/prof_conv.py; not re-measured by this run
+NCU_CAPTURE = {(512, 64): {"traffic": 1.458739e9 + 1.048327e9, "tensor_pipe_active_pct": 95.1,
+                           "file": "profiles/r01b_ncu_conv_fprop_3x3_512_B64.txt"}}
 
 
 def _peaks():
@@ -39,10 +49,27 @@ def _peaks():
         return None
 
 
+def executed_gflop_per_image(feat, latent, heads=8):
+    """GEMM work the step actually issues per image (dead work pruned): 3x3 / 1x1 convs of the trunk in
+    both Teacher passes, the K/V-free attention GEMMs on the surviving rows, the executed backward (conv2 dgrad + wgrad
+    and proj wgrad of blocks 1,2, shortcut wgrad), feature extractor, and 3x the VAE forward."""
+    C, P = feat, 16384
+    nq = P // 32 + 31
+    nq_pad = (nq + 7) // 8 * 8
+    conv = lambda cin, cout, k: 2.0 * P * cin * cout * k * k
+    fold = 2.0 * nq_pad * C * (heads * C) + 2.0 * nq_pad * C * C + 2.0 * nq_pad * C * C + nq * 2 * 2.0 * 32 * heads * C
+    fwd_expert = conv(128, C, 3) + conv(128, C, 1) + 5 * conv(C, C, 3) + 3 * fold
+    fe = 1.08e9
+    fwd = 4 * fwd_expert + fe
+    bwd = 4 * (2 * (2 * conv(C, C, 3) + 2.0 * nq_pad * C * C) + conv(128, C, 1))
+    vae = 3 * (4.09e9 if latent == 512 else 4.04e9)
+    return (2 * fwd + bwd + vae) / 1e9
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during a timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -55,6 +82,7 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -72,16 +100,36 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        pw = []
+        for r in self.rows:
+            try:
+                pw.append(float(r[6]))
+            except Exception:
+                pass
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w_median": sorted(pw)[len(pw) // 2] if pw else None}
 
 
-def _args_ns(batch, latent, emb, feat):
+def _args_ns(batch, latent, emb, feat, data_dir="synthetic", accum=1):
     from lunaris_orion_b200.train_hybrid import build_arg_parser
     return build_arg_parser().parse_args([
-        "--data_dir", "synthetic", "--batch_size", str(batch), "--gradient_accumulation_steps", "1",
+        "--data_dir", data_dir, "--batch_size", str(batch), "--gradient_accumulation_steps", str(accum),
         "--latent_dim", str(latent), "--embedding_dim", str(emb), "--feature_dim", str(feat),
         "--vae_lr", "3e-4", "--teacher_lr", "2e-4"])
+
+
+def _write_sprite_files(d, n, files=2):
+    """The reference's on-disk format (generate.py:858-904): sprites_*.npy uint8 NHWC + labels_*.csv, SURVEY 8(d) data."""
+    import numpy as np
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(1234)
+    per = (n + files - 1) // files
+    for k in range(files):
+        np.save(os.path.join(d, f"sprites_{k:03d}.npy"), rng.integers(0, 256, (per, 128, 128, 3), dtype=np.uint8))
+        with open(os.path.join(d, f"labels_{k:03d}.csv"), "w") as f:
+            f.write("filename,category,prompt,seed,pixel_size,guidance_scale,pag_scale,num_steps\n")
+            for i in range(per):
+                f.write(f"s{k}_{i}.png,cat,prompt,{i},8,7.5,3.0,20\n")
 
 
 # ====================================================================================================== our arm
@@ -91,21 +139,26 @@ def run_ours(a):
     import torch.distributed as dist
     from lunaris_orion_b200 import _capi, ops
     from lunaris_orion_b200.train_hybrid import TrainingManager
-    from lunaris_orion_b200.lunar_generate import sprites_to_tensor
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    if world != a.gpus:
-        if a.gpus != 1:
-            raise SystemExit(f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks (WORLD_SIZE={world})")
+    if world != a.gpus and a.gpus != 1:
+        raise SystemExit(f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks (WORLD_SIZE={world})")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     B = a.batch
-    tm = TrainingManager(_args_ns(B, a.latent, a.emb, a.feat), device=dev)
+    data_dir = os.path.join(tempfile.gettempdir(), "lunaris_bench_sprites_%s" % os.environ.get("MASTER_PORT", "solo"))
+    if rank == 0:
+        _write_sprite_files(data_dir, int(math.ceil(world * B * 4 / 0.9)) + 2)
+    if world > 1:
+        dist.barrier()
+    tm = TrainingManager(_args_ns(B, a.latent, a.emb, a.feat, data_dir=data_dir), device=dev)
     lib = _capi.lib()
 
     rng = np.random.default_rng(1234 + rank)
-    host_u8 = torch.from_numpy(rng.integers(0, 256, (4, B, 128, 128, 3), dtype=np.uint8)).pin_memory()
+    host_u8 = torch.from_numpy(rng.integers(0, 256, (4, B, 128, 128, 3), dtype=np.uint8))
     dev_imgs = [(host_u8[i].to(dev).permute(0, 3, 1, 2).float() / 127.5 - 1.0).contiguous() for i in range(4)]
 
     def barrier():
@@ -116,77 +169,116 @@ def run_ours(a):
     def timed(step_fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local).start() if rank == 0 else None
         e0.record()
         for i in range(steps):
             step_fn(i)
         e1.record()
         barrier()
+        clocks = sampler.stop() if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), clocks
 
     def step_resident(i):
         tm._process_batch(dev_imgs[i % 4], i, return_tensor=True)
 
     host_metrics = torch.empty(12, dtype=torch.float32).pin_memory()
+    batches = tm.train_loader.forever()
 
     def step_e2e(i):
-        x = sprites_to_tensor(host_u8[i % 4].to(dev, non_blocking=True))
+        x = next(batches)                                  # disk (page cache) -> pinned -> H2D -> normalise kernel
         m = tm._process_batch(x, i, return_tensor=True)
         host_metrics.copy_(m, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        return float(host_metrics[0])                      # the step's result is read on the host
 
     for i in range(a.warmup):
         step_resident(i)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = lib.lun_launch_count()
-    ms = timed(step_resident, a.steps)
+    ms, clocks = timed(step_resident, a.steps)
     launches = lib.lun_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     step_e2e(0)
-    ms_e2e = timed(step_e2e, a.steps)
+    ms_e2e, clocks_e2e = timed(step_e2e, a.steps)
     metrics = dict(zip(("recon_loss", "kl_loss", "quality_loss"), host_metrics[:3].tolist()))
+    ms_again, clocks_again = timed(step_resident, a.steps)         # A-B-A: drift / ordering between the two loops
 
-    # ---- roofline of the dominant kernel, timed alone on this stream
+    # ---- data-parallel check (one extra, untimed step)
+    dp_check = None
+    if world > 1:
+        dp_check = _dp_check(tm, dev_imgs[0], world, dev)
+
+    # ---- roofline of the dominant kernel, timed alone on this stream, with cuDNN on the same shape beside it
     roof = None
     if rank == 0:
         C = a.feat
         x = torch.randn(B, 128, 128, C, device=dev).to(torch.bfloat16)
-        wp = ops.pack_conv_weight(torch.randn(C, C, 3, 3, device=dev) * 0.02)
+        w = torch.randn(C, C, 3, 3, device=dev) * 0.02
+        wp = ops.pack_conv_weight(w)
         bias = torch.zeros(C, device=dev)
         st = torch.zeros(2 * C, device=dev)
         y = torch.empty(B, 128, 128, C, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):
-            ops.conv2d_fprop(x, wp, 3, 1, 1, bias=bias, act_leaky=True, stats=st, out=y)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(10):
-            ops.conv2d_fprop(x, wp, 3, 1, 1, bias=bias, act_leaky=True, stats=st, out=y)
-        e1.record()
-        torch.cuda.synchronize()
-        kms = e0.elapsed_time(e1) / 10
+
+        def time_it(fn, n=10):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        kms = time_it(lambda: ops.conv2d_fprop(x, wp, 3, 1, 1, bias=bias, act_leaky=True, stats=st, out=y))
         fl = 2.0 * B * 16384 * C * C * 9
         pk = _peaks()
         peak = pk["bf16_tflops"] if pk else 1590.0
-        roof = {"bound": "tensor", "kernel": "conv_fprop_kernel 3x3 %d->%d @128x128 B=%d (bias+LeakyReLU+BN stats)" % (C, C, B),
-                "achieved": round(fl / kms / 1e9, 1), "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if pk else "fallback",
-                "unit": "TFLOP/s", "frac": round(fl / kms / 1e9 / peak, 4), "traffic": NCU_TRAFFIC.get((C, B)),
-                "tensor_pipe_active_pct_ncu": NCU_TENSOR_PCT.get((C, B)), "ms_per_launch": round(kms, 4),
-                "step_model_flop_frac_of_sustained": None}
+        cap = NCU_CAPTURE.get((C, B), {})
+        roof = {"bound": "tensor",
+                "kernel": "conv_fprop_kernel 3x3 %d->%d @128x128 B=%d (bias+LeakyReLU+BN stats)" % (C, C, B),
+                "achieved": round(fl / kms / 1e9, 1), "peak": peak,
+                "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if pk else "fallback",
+                "unit": "TFLOP/s", "frac": round(fl / kms / 1e9 / peak, 4), "ms_per_launch": round(kms, 4),
+                "traffic": cap.get("traffic"), "traffic_source": cap.get("file"),
+                "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_active_pct")}
+        if world == 1 and not a.no_extras:
+            try:                                           # cuDNN: the reference's kernel for this call site
+                import torch.nn.functional as F
+                torch.backends.cudnn.benchmark = True
+                xc = x.permute(0, 3, 1, 2)                 # NHWC storage = channels_last
+                wc = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                bc = bias.to(torch.bfloat16)
+                cms = time_it(lambda: F.conv2d(xc, wc, bc, padding=1))
+                roof["vs_cudnn"] = {"cudnn_tflops": round(fl / cms / 1e9, 1), "cudnn_ms": round(cms, 4),
+                                    "ratio": round(cms / kms, 3),
+                                    "note": "torch F.conv2d bf16 channels_last, cudnn.benchmark on, bias only (no "
+                                            "LeakyReLU / BN statistics, which ours computes in the same launch)"}
+            except Exception as e:                         # pragma: no cover
+                roof["vs_cudnn"] = {"error": str(e)[:200]}
         del x, y
+
+    extras = {}
+    if world == 1 and not a.no_extras:
+        extras["c5"] = _bench_c5(tm, dev)
+        extras["c2"] = _bench_c2(dev)
 
     if rank != 0:
         return
     n_img = B * world * a.steps
     value = n_img / (ms / 1e3)
     pk = _peaks()
-    if roof is not None and pk:
-        roof["step_model_flop_frac_of_sustained"] = round(value / world * GF_PER_IMG / 1e3 / pk["bf16_tflops_sustained"], 4) \
-            if (a.feat, a.latent) == (512, 512) else None
+    if roof is not None and pk and (a.feat, a.latent) == (512, 512):
+        sus = pk["bf16_tflops_sustained"]
+        per_gpu = value / world
+        ex = executed_gflop_per_image(a.feat, a.latent)
+        roof["step_algorithmic_gflop_per_img"] = GF_PER_IMG
+        roof["step_executed_gflop_per_img"] = round(ex, 1)
+        # algorithmic: the reference's op sequence incl. the dead work this path prunes (NOT a utilisation);
+        # executed: GEMM FLOPs actually issued / sustained cuBLAS rate
+        roof["step_algorithmic_flop_frac_of_sustained"] = round(per_gpu * GF_PER_IMG / 1e3 / sus, 4)
+        roof["step_executed_flop_frac_of_sustained"] = round(per_gpu * ex / 1e3 / sus, 4)
     line = {
         "metric": "train images/sec @128x128 bf16 (hybrid VAE+Teacher step)", "value": round(value, 2),
         "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -198,107 +290,230 @@ def run_ours(a):
                                   B, a.latent, a.emb, a.feat),
                    "global_batch": B * world, "parallelism": "dp%d" % world, "l2": "working set >> 126 MB L2"},
         "e2e": {"value": round(n_img / (ms_e2e / 1e3), 2), "unit": "images/s",
-                "h2d_bytes_per_step": B * 128 * 128 * 3, "d2h_bytes_per_step": 48},
+                "h2d_bytes_per_step": tm.train_loader.h2d_bytes_per_batch, "d2h_bytes_per_step": 48,
+                "ms_per_step": round(ms_e2e / a.steps, 3), "clocks": clocks_e2e,
+                "path": "sprites_*.npy on disk -> SpriteLoader (mmap gather, pinned ring, copy stream) -> "
+                        "lun_sprites_u8_to_f32 -> TrainingManager._process_batch -> 12 metrics read on the host"},
+        "value_repeat_after_e2e": {"value": round(n_img / (ms_again / 1e3), 2), "ms_per_step": round(ms_again / a.steps, 3),
+                                   "clocks": clocks_again,
+                                   "note": "same resident loop run again after the e2e loop (A-B-A): the spread "
+                                           "between the two resident runs bounds what ordering / clock drift explains"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "last_metrics": metrics,
     }
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+    line.update(extras)
     if world == 1 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(a, steps=1, warmup=0)
+        line["cpu_baseline"] = cpu_reference(a, steps=1, warmup=1, batch=a.cpu_batch_sample, budget_s=60.0)
     print(json.dumps(line), flush=True)
 
 
-# ====================================================================================================== reference arm
-def cpu_reference(a, steps, warmup, budget_s=150.0):
-    """Oracle port of the reference's CPU path (torch fp32, all host threads): full steps on batch `--cpu-batch`
-    (default 4) of the same architecture, at most `budget_s` seconds of them. Returns the cpu_baseline object."""
+def _dp_check(tm, images, world, dev):
+    """SURVEY.md 8(e) parity: DP gradients == mean over ranks of the per-rank gradients; identical parameters."""
     import torch
-    from oracle import restatement as R
-    from lunaris_orion_b200.lunar_evaluator import LunarMoETeacher
-    from lunaris_orion_b200.lunar_generate import LunarisCoreVAE
+    import torch.distributed as dist
+    res = {}
+
+    def after_reduce(t):
+        worst, n = 0.0, 0
+        for i, flat in enumerate(t.reducer.flat):
+            local = t.reducer.local[i]
+            gathered = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(gathered, local)
+            mean = torch.stack(gathered).double().mean(0)
+            got = flat.double() / world                    # buckets hold SUMS; the optimizer folds 1/world in
+            scale = mean.abs().max().item() + 1e-30
+            worst = max(worst, (got - mean).abs().max().item() / scale)
+            n += len(t.reducer.buckets[i])
+            differs = (gathered[0] - gathered[-1]).abs().max().item() > 0
+            res["ranks_hold_different_local_grads"] = res.get("ranks_hold_different_local_grads", False) or differs
+        res["grad_vs_mean_of_rank_grads_max_rel"] = worst
+        res["tensors_checked"] = n
+    tm.reducer.keep_local = True
+    tm._after_reduce = after_reduce
+    tm._process_batch(images, 0, return_tensor=True)
+    tm.reducer.keep_local = False
+    tm._after_reduce = None
+    tm.reducer.local.clear()
+    worst = torch.zeros(1, device=dev)
+    n = 0
+    for m in (tm.vae, tm.teacher):
+        for p in m.parameters():
+            ref = p.detach().clone()
+            dist.broadcast(ref, 0)
+            worst = torch.maximum(worst, (p.detach() - ref).abs().max().reshape(1))
+            n += 1
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    res["max_abs_param_diff_vs_rank0"] = float(worst.item())
+    res["params_bit_identical_across_ranks"] = float(worst.item()) == 0.0
+    res["param_tensors_compared"] = n
+    res["ok"] = bool(res["params_bit_identical_across_ranks"] and res["grad_vs_mean_of_rank_grads_max_rel"] < 1e-5
+                     and res["ranks_hold_different_local_grads"])
+    return res
+
+
+def _bench_c5(tm, dev):
+    """BASELINE.json configs[4]: decoder-only sampling (lunar_generate.py:278-291), batch 256, latent 512."""
+    import torch
+    n, iters = 256, 20
+    with torch.no_grad():
+        for _ in range(3):
+            tm.vae.sample(n)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            tm.vae.sample(n)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    ips = n / ms * 1e3
+    pk = _peaks() or {"bf16_tflops_sustained": 1331.6, "hbm_gbs": 6556.2}
+    return {"metric": "decoder-only sampling images/sec (batch 256, latent %d)" % tm.vae.latent_dim,
+            "value": round(ips, 1), "unit": "images/s", "ms_per_batch": round(ms, 4),
+            "tensor_frac_of_sustained": round(ips * 1.136e9 / 1e12 / pk["bf16_tflops_sustained"], 4),
+            "hbm_frac_of_peak": round(ips * 4.3e6 / 1e9 / pk["hbm_gbs"], 4),
+            "model": "1.136 GFLOP and ~4.3 MB of compulsory traffic per image (SURVEY.md 8d); includes torch.randn of z"}
+
+
+def _bench_c2(dev):
+    """BASELINE.json configs[1]: batch 16, latent 256 / emb 128 / feat 256, --gradient_accumulation_steps 4."""
+    import torch
+    from lunaris_orion_b200.train_hybrid import TrainingManager
+    B, accum = 16, 4
+    tm = TrainingManager(_args_ns(B, 256, 128, 256, accum=accum), device=dev)
+    xs = [torch.rand(B, 3, 128, 128, device=dev) * 2 - 1 for _ in range(4)]
+    for i in range(2 * accum):
+        tm._process_batch(xs[i % 4], i, return_tensor=True)
+    calls = 8 * accum
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(calls):
+        tm._process_batch(xs[i % 4], i, return_tensor=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / calls
+    ips = B / ms * 1e3
+    pk = _peaks() or {"bf16_tflops_sustained": 1331.6}
+    return {"metric": "train images/sec, batch 16, accumulation 4, feat 256 (every micro-batch counted)",
+            "value": round(ips, 1), "unit": "images/s", "ms_per_micro_batch": round(ms, 3),
+            "algorithmic_flop_frac_of_sustained": round(ips * GF_PER_IMG_C2 / 1e3 / pk["bf16_tflops_sustained"], 4)}
+
+
+# ====================================================================================================== reference arm
+def cpu_reference(a, steps, warmup, batch, budget_s=150.0):
+    """The reference's own CPU path on the host cores. With oracle/_ref (or /root/reference) present: the UNMODIFIED
+    reference TrainingManager built by its own main() (--force_cpu, dropout on, AdamW, schedulers; SURVEY.md App. C.1
+    harness) - every step is one real `_process_batch` on a bounded batch of the benchmarked architecture.
+    Otherwise (kind "port") the oracle restatement. Returns the cpu_baseline object."""
+    import torch
+    from oracle import reference_loader
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(42)
-    vae = LunarisCoreVAE(a.latent)
-    teacher = LunarMoETeacher(feature_dim=a.feat, embedding_dim=a.emb, dropout_rate=0.0)
+    if reference_loader.available():
+        from oracle import ref_harness
+        d = tempfile.mkdtemp(prefix="lunaris_ref_")
+        ref_harness.write_sprites(os.path.join(d, "data"), max(10, int(math.ceil(batch / 0.9)) + 1))
+        cfg = dict(B=batch, latent=a.latent, emb=a.emb, feat=a.feat, seed=42, vae_lr=3e-4, teacher_lr=2e-4)
+        import contextlib
+        import io
+        import logging
+        with contextlib.redirect_stdout(io.StringIO()):
+            tm = ref_harness.drive_reference_trainer(cfg, os.path.join(d, "data"), os.path.join(d, "out"))
+        logging.disable(logging.CRITICAL)
+        g = torch.Generator().manual_seed(7)
+        x = torch.randint(0, 256, (batch, 3, 128, 128), generator=g, dtype=torch.uint8).float() / 127.5 - 1.0
+        one = lambda i: tm._process_batch(x.clone(), i)
+        kind = "reference"
+        what = ("UNMODIFIED reference train_hybrid.TrainingManager._process_batch (--force_cpu, fp32, dropout on, clip "
+                "+ AdamW + scheduler) from %s" % ("oracle/_ref bytecode" if reference_loader.kind() == "bytecode"
+                                                   else reference_loader.REF))
+    else:
+        from oracle import restatement as R
+        from lunaris_orion_b200.lunar_evaluator import LunarMoETeacher
+        from lunaris_orion_b200.lunar_generate import LunarisCoreVAE
+        torch.manual_seed(42)
+        vae = LunarisCoreVAE(a.latent)
+        teacher = LunarMoETeacher(feature_dim=a.feat, embedding_dim=a.emb, dropout_rate=0.0)
 
-    def leaf_sd(m):
-        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-        for n, _ in m.named_parameters():
-            sd[n].requires_grad_(True)
-        return sd
-    vsd, tsd = leaf_sd(vae), leaf_sd(teacher)
-    Bs = a.cpu_batch
-    x = torch.rand(Bs, 3, 128, 128) * 2 - 1
+        def leaf_sd(m):
+            sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+            for n, _ in m.named_parameters():
+                sd[n].requires_grad_(True)
+            return sd
+        vsd, tsd = leaf_sd(vae), leaf_sd(teacher)
+        x = torch.rand(batch, 3, 128, 128) * 2 - 1
 
-    def one():
-        for sd in (vsd, tsd):
-            for v in sd.values():
-                v.grad = None
-        R.train_step(x, vsd, tsd, torch.randn(Bs, a.latent))
-    t_first = None
-    for _ in range(warmup):
-        t0 = time.time()
-        one()
-        t_first = time.time() - t0
+        def one(i):
+            for sd in (vsd, tsd):
+                for v in sd.values():
+                    v.grad = None
+            R.train_step(x, vsd, tsd, torch.randn(batch, a.latent))
+        kind = "port"
+        what = "oracle/restatement.py train_step (reference unavailable on this box: oracle/_ref missing)"
+    for i in range(warmup):
+        one(i)
     done, t_total = 0, 0.0
-    for _ in range(steps):
+    for i in range(steps):
         t0 = time.time()
-        one()
+        one(warmup + i)
         t_total += time.time() - t0
         done += 1
         if t_total + (t_total / done) > budget_s:
             break
-    val = Bs * done / t_total
-    return {"value": round(val, 4), "unit": "images/s", "cores": cores, "kind": "port", "timed_steps": done,
-            "sample": "oracle/restatement.py train_step (VAE fwd/bwd, Teacher pass A + pass B + bwd) on batch %d of the "
-                      "C3 architecture, fp32, %d threads, %.1f s/step" % (Bs, torch.get_num_threads(), t_total / done)}
+    val = batch * done / t_total
+    return {"value": round(val, 4), "unit": "images/s", "cores": cores, "kind": kind, "timed_steps": done,
+            "warmup_steps": warmup, "batch": batch,
+            "sample": "%s; %d timed step(s) after %d warm-up on batch %d of the C3 architecture (latent %d, emb %d, feat "
+                      "%d), %d threads, %.1f s/step" % (what, done, warmup, batch, a.latent, a.emb, a.feat,
+                                                        torch.get_num_threads(), t_total / done)}
 
 
 def eager_gpu_reference(a):
-    """SURVEY.md 8(d) "existing kernel" bar: the reference's op sequence (oracle port, loop-free, so faster than the
-    reference's own 16k-iteration Python loop) as stock PyTorch eager kernels under bf16 autocast on this B200:
-    cuDNN / cuBLAS / ATen, no kernel of this repo. Reported beside, never instead of, the CPU reference arm."""
+    """SURVEY.md 8(d) "existing kernel" bar: the UNMODIFIED reference trainer on this B200 as stock PyTorch eager
+    kernels (cuDNN / cuBLAS / ATen, its own 16k-iteration attention loop), bf16 autocast recipe of SURVEY 8(c):
+    `torch.set_autocast_dtype('cuda', bf16)` before the reference modules are imported (their decorators freeze the
+    dtype at import) and an outer bf16 autocast around `_process_batch`. Never the driver's arm."""
+    import contextlib
+    import io
+    import logging
     import torch
-    from oracle import restatement as R
-    from lunaris_orion_b200.lunar_evaluator import LunarMoETeacher
-    from lunaris_orion_b200.lunar_generate import LunarisCoreVAE
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    torch.manual_seed(42)
-    vae = LunarisCoreVAE(a.latent)
-    teacher = LunarMoETeacher(feature_dim=a.feat, embedding_dim=a.emb, dropout_rate=0.0)
-
-    def leaf_sd(m):
-        sd = {k: v.detach().clone().to(dev) for k, v in m.state_dict().items()}
-        for n, _ in m.named_parameters():
-            sd[n].requires_grad_(True)
-        return sd
-    vsd, tsd = leaf_sd(vae), leaf_sd(teacher)
+    from oracle import ref_harness, reference_loader
+    if not reference_loader.available():
+        print(json.dumps({"impl": "reference", "device": "cuda-eager", "unavailable": "oracle/_ref missing"}))
+        return
+    torch.set_autocast_dtype("cuda", torch.bfloat16)
     Bs = a.eager_batch
+    d = tempfile.mkdtemp(prefix="lunaris_ref_")
+    ref_harness.write_sprites(os.path.join(d, "data"), int(math.ceil(Bs / 0.9)) + 2)
+    cfg = dict(B=Bs, latent=a.latent, emb=a.emb, feat=a.feat, seed=42, vae_lr=3e-4, teacher_lr=2e-4)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tm = ref_harness.drive_reference_trainer(cfg, os.path.join(d, "data"), os.path.join(d, "out"), device="cuda")
+    logging.disable(logging.CRITICAL)
+    dev = tm.device
     x = torch.rand(Bs, 3, 128, 128, device=dev) * 2 - 1
-    torch.backends.cudnn.benchmark = True
 
-    def one():
-        for sd in (vsd, tsd):
-            for v in sd.values():
-                v.grad = None
+    def one(i):
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            R.train_step(x, vsd, tsd, torch.randn(Bs, a.latent, device=dev))
-    for _ in range(max(a.warmup, 2)):
-        one()
+            tm._process_batch(x, i)
+    for i in range(max(min(a.warmup, 2), 1)):
+        one(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
-        one()
+    for i in range(a.steps):
+        one(i)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     print(json.dumps({
-        "impl": "reference", "device": "cuda-eager", "metric": "train images/sec @128x128 bf16 (hybrid VAE+Teacher step)",
-        "value": round(Bs / ms * 1e3, 2), "unit": "images/s", "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 2),
+        "impl": "reference", "device": "cuda-eager", "kind": "reference",
+        "metric": "train images/sec @128x128 bf16 (hybrid VAE+Teacher step)",
+        "value": round(Bs / ms * 1e3, 2), "unit": "images/s", "n_gpus": 1, "steps": a.steps,
         "ms_per_step": round(ms, 2), "higher_is_better": True, "dtype": "bf16 autocast", "data": "synthetic",
-        "config": {"workload": "C3 architecture (latent %d, emb %d, feat %d), batch %d; oracle port of the reference op "
-                               "sequence (no optimizer step, no dropout RNG) on stock PyTorch eager kernels"
-                               % (a.latent, a.emb, a.feat, Bs)},
+        "config": {"workload": "C3 architecture (latent %d, emb %d, feat %d), batch %d; UNMODIFIED reference "
+                               "TrainingManager._process_batch on stock PyTorch eager kernels" % (a.latent, a.emb, a.feat, Bs)},
         "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}), flush=True)
 
 
@@ -308,15 +523,16 @@ def run_reference(a):
         return
     if a.ref_device == "cuda":
         return eager_gpu_reference(a)
-    cb = cpu_reference(a, steps=a.steps, warmup=min(a.warmup, 1))
+    cb = cpu_reference(a, steps=a.steps, warmup=min(a.warmup, 1), batch=a.cpu_batch, budget_s=a.ref_budget)
     line = {
         "impl": "reference", "metric": "train images/sec @128x128 bf16 (hybrid VAE+Teacher step)",
-        "value": cb["value"], "unit": "images/s", "n_gpus": a.gpus, "steps": cb["timed_steps"], "warmup": min(a.warmup, 1),
-        "ms_per_step": round(1e3 * a.cpu_batch / cb["value"], 1), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "value": cb["value"], "unit": "images/s", "n_gpus": a.gpus, "steps": cb["timed_steps"],
+        "warmup": cb["warmup_steps"], "ms_per_step": round(1e3 * a.cpu_batch / cb["value"], 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C3 high-end architecture (latent %d, emb %d, feat %d), reference CPU path on host cores; "
-                               "each step = one full _process_batch on a bounded sample of batch %d"
-                               % (a.latent, a.emb, a.feat, a.cpu_batch)},
+                               "each step = one full _process_batch on a bounded sample of batch %d (a batch-64 step "
+                               "of the reference takes tens of minutes on CPU; steps stop at a %d s budget)"
+                               % (a.latent, a.emb, a.feat, a.cpu_batch, int(a.ref_budget))},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -333,10 +549,16 @@ def main():
     p.add_argument("--latent", type=int, default=CFG["latent"])
     p.add_argument("--emb", type=int, default=CFG["emb"])
     p.add_argument("--feat", type=int, default=CFG["feat"])
-    p.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4)
+    p.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4,
+                   help="--impl reference: batch of each reference step (bounded sample of the 64-image workload)")
+    p.add_argument("--cpu-batch-sample", dest="cpu_batch_sample", type=int, default=1,
+                   help="batch of the cpu_baseline object inside our own line (about 10-30 s of CPU work)")
+    p.add_argument("--ref-budget", dest="ref_budget", type=float, default=170.0,
+                   help="--impl reference: stop timing new steps once this many seconds are spent")
     p.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    p.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the c2 / c5 / vs_cudnn sub-runs")
     p.add_argument("--ref-device", dest="ref_device", default="cpu", choices=["cpu", "cuda"],
-                   help="--impl reference only: 'cuda' times the same op sequence as stock PyTorch eager kernels on the GPU")
+                   help="--impl reference only: 'cuda' times the unmodified reference as stock PyTorch eager kernels on the GPU")
     p.add_argument("--eager-batch", dest="eager_batch", type=int, default=16)
     a = p.parse_args()
     if a.impl == "reference":

@@ -3,7 +3,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblunaris_b200.so")
+# LUNARIS_B200_LIB selects another build of the SAME library (tools/gpu A/B runs of a kernel change against its
+# predecessor on one box); it is not a fallback: a missing file raises like the default path does.
+LIB_PATH = os.environ.get("LUNARIS_B200_LIB") or os.path.join(_HERE, "_lib", "liblunaris_b200.so")
 
 _ERRORS = {
     2: "LUN_E_SHAPE: unsupported channel count / block size",
