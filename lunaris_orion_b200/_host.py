@@ -7,10 +7,11 @@ import torch
 from ._capi import LunarisB200Error
 
 # ------------------------------------------------------------------------------------------------ operand cache
-# bf16 kernel-layout shadows of fp32 parameters. Entries hang off the parameter (or module) through weak keys, so they
-# die with the model; they are valid for one (version counter, storage address, device) of every source tensor:
-# optimizer steps bump the version, `.to()` / `p.data = w` change the address.
-_cache = weakref.WeakKeyDictionary()
+# bf16 kernel-layout shadows of fp32 parameters. Entries are keyed by the owner's id and guarded by a weak reference
+# whose callback drops them, so they die with the model (a WeakKeyDictionary cannot hold tensors: its key comparison
+# falls back to `==`, which is elementwise). An entry is valid for one (version counter, storage address, device) of
+# every source tensor: optimizer steps bump the version, `.to()` / `p.data = w` change the address.
+_cache = {}
 
 
 def _stamp(tensors):
@@ -20,13 +21,16 @@ def _stamp(tensors):
 def cached(owner, kind, sources, build):
     """build() memoised per (owner, kind) while every tensor of `sources` is unchanged. `owner` is any weak-referenceable
     object whose lifetime bounds the entry (a Parameter or a Module)."""
-    slot = _cache.get(owner)
-    if slot is None:
-        slot = _cache[owner] = {}
+    key = id(owner)
+    ent = _cache.get(key)
+    if ent is None or ent[0]() is not owner:              # first use, or a recycled id
+        ent = (weakref.ref(owner, lambda _, key=key: _cache.pop(key, None)), {})
+        _cache[key] = ent
+    slot = ent[1]
     stamp = _stamp(sources)
-    ent = slot.get(kind)
-    if ent is not None and ent[0] == stamp:
-        return ent[1]
+    hit = slot.get(kind)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
     val = build()
     slot[kind] = (stamp, val)
     return val

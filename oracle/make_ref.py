@@ -3,9 +3,10 @@ lie under /root/reference, so the real reference trainer travels to the GPU box 
 
     python oracle/make_ref.py            (also run by __graft_entry__.build() when /root/reference is present)
 
-Outputs only compiled artefacts - sourceless `*.pyc` files for the three modules on the hot path
-(lunar_generate, lunar_evaluator, train_hybrid) - into the git-ignored oracle/_ref/. No reference source is copied into
-the repository or its history. The GPU box runs the same image (same CPython), so the bytecode imports there.
+Outputs only compiled artefacts - sourceless CPython bytecode of the three modules on the hot path (lunar_generate,
+lunar_evaluator, train_hybrid), stored as `*.rbc` (plain .pyc contents; the .pyc suffix is filtered out of gpurun
+snapshots) - into the git-ignored oracle/_ref/. No reference source is copied into the repository or its history. The
+GPU box runs the same image (same CPython), so the bytecode imports there through oracle/reference_loader.py.
 TEST / BENCH INFRASTRUCTURE ONLY: consumers are tests/, bench.py's `--impl reference` and `cpu_baseline` legs.
 """
 import os
@@ -24,7 +25,7 @@ def stage(verbose=False):
         return None
     os.makedirs(OUT, exist_ok=True)
     for m in MODULES:
-        dst = os.path.join(OUT, m + ".pyc")
+        dst = os.path.join(OUT, m + ".rbc")
         py_compile.compile(os.path.join(SRC, m + ".py"), cfile=dst, dfile=f"<reference>/{m}.py", doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
         if verbose:

@@ -38,10 +38,9 @@ def import_reference_trainer(dropin=False):
             if name in sys.modules:
                 raise RuntimeError(f"{name} is already imported: use a fresh process for the drop-in seam")
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        sys.path.insert(0, reference_loader.REF)
         sys.path.insert(0, os.path.join(root, "lunaris_orion_b200", "dropin"))
-    elif reference_loader.REF not in sys.path:
-        sys.path.insert(0, reference_loader.REF)
+    # the reference directory is consulted last (sources and oracle/_ref bytecode alike), after everything on sys.path
+    reference_loader.install_finder()
     import train_hybrid as th
     if not getattr(th, "_lun_dl_shim", False):
         _DL = th.DataLoader

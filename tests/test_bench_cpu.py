@@ -40,7 +40,7 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_runs_from_the_staged_bytecode_alone():
     """What the GPU box has: no /root/reference, only oracle/_ref/*.pyc (oracle/make_ref.py)."""
     ref = os.path.join(ROOT, "oracle", "_ref")
-    if not os.path.isfile(os.path.join(ref, "train_hybrid.pyc")):
+    if not os.path.isfile(os.path.join(ref, "train_hybrid.rbc")):
         import pytest
         pytest.skip("oracle/_ref not built")
     r = _run(["--impl", "reference"] + SMALL, env={"LUNARIS_REFERENCE": ref})
