@@ -253,6 +253,35 @@ int lun_flash_attn2d_dqk_bf16(const void* qk, const void* v, const void* dy, con
  * [T][B][A] (transpose = 1), the K-major slabs lun_conv_taps_bf16 / lun_convT4x4s2_bf16 read. */
 int lun_pack_weight_bf16(const float* src, void* dst, int A, int B, int T, int transpose, void* stream);
 
+/* `heads` independent GEMMs in ONE launch of the tap-list kernel (grouped mode): out[r, h*cout + n] = bias[h*cout + n] +
+ * sum_k x[r, h*cin + k] * w[h][n][k]; x [rows, heads*cin] bf16, w [heads][cout][cin] bf16, out [rows, heads*cout] bf16.
+ * Replaces the value projection of the as-executed attention (lunar_evaluator.py:153-156, 213) on the surviving rows:
+ * one [hd, C] GEMM per head instead of a block-diagonal [C, heads*C] one that multiplies 7/8 zeros. heads <= 16. */
+int lun_head_linear_bf16(const void* x, int rows, int heads, int cin, const void* w, int cout, const float* bias,
+                         void* out, void* stream);
+
+/* Teacher heads (lunar_evaluator.py:353-397, 417-456): gate, quality heads, semantic head, style / prompt nets and the
+ * mixing between them, fp32, on the pooled per-image channel SUMS of the trunk (the 1 / (H W) of AdaptiveAvgPool2d is
+ * inv_hw). One launch forward, two launches backward.
+ *   params / grads: 6 pointers per head {ln_w, ln_b, w1, b1, w2, b2} (torch layouts [out, in]; ln_* null for the gate),
+ *     heads in the order gate, quality[0..E), semantic, style, prompt -> (E + 4) * 6 entries; a null grads entry means
+ *     "not wanted";
+ *   dims: {B, E, F, C, emb, gate_hidden, quality_hidden, semantic_hidden, style_hidden, prompt_hidden};
+ *   seeds: E + 4 dropout seeds of the counter RNG (element index = sample * hidden + unit), used when drop_p > 0;
+ *   pooled_fe [B, F], pooled [E][B][C] sums; outputs quality [B,4] (sigmoid), weights [B,E] (softmax), style / prompt
+ *   [B, emb], semantic [B,1]; save [B, sizes[0]] keeps what the backward needs (null in eval);
+ *   backward work buffers: dpre [B, sizes[1]], dout2 [B, sizes[2]], dxn [(E + 3), B, C] floats (lun_heads_buffer_sizes);
+ *   g_*: incoming gradients of the five outputs (any may be null); d_pooled [E][B][C]: gradient of the pooled sums. */
+int lun_heads_buffer_sizes(const int* dims, int* sizes);
+int lun_heads_fwd(const void* const* params, const int* dims, const unsigned long long* seeds, float inv_hw, float slope,
+                  float drop_p, int training, const float* pooled_fe, const float* pooled, float* quality,
+                  float* weights, float* style, float* prompt, float* semantic, float* save, void* stream);
+int lun_heads_bwd(const void* const* params, const int* dims, const unsigned long long* seeds, float inv_hw, float slope,
+                  float drop_p, const float* pooled_fe, const float* pooled, const float* weights, const float* save,
+                  const float* g_quality, const float* g_weights, const float* g_style, const float* g_prompt,
+                  const float* g_semantic, float* dpre, float* dout2, float* dxn, float* d_pooled, void* const* grads,
+                  void* stream);
+
 /* Optimizer boundary (train_hybrid.py:906-922): clip_grad_norm_(max_norm) + AdamW over all tensors of one model in two
  * multi-tensor launches. table: device array of 72-byte rows {float* param, grad, exp_avg, exp_avg_sq; long long numel;
  * float lr, beta1, beta2, eps, weight_decay, bias_c1 = 1 - beta1^t, bias_c2_sqrt = sqrt(1 - beta2^t), pad} - hyper-

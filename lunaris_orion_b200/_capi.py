@@ -111,6 +111,13 @@ SIGNATURES = {
     "lun_flash_attn2d_dqk_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_void_p],
     "lun_pack_weight_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "lun_head_linear_bf16": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "lun_heads_buffer_sizes": [c_int_p, c_int_p],
+    "lun_heads_fwd": [c_pp, c_int_p, ctypes.POINTER(c_u64), c_float, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "lun_heads_bwd": [c_pp, c_int_p, ctypes.POINTER(c_u64), c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                      c_pp, c_void_p],
     "lun_multi_grad_sumsq": [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p],
     "lun_multi_clip_adamw": [c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_void_p],
     "lun_fe_branches": [c_void_p, c_void_p, c_void_p, c_pp, c_pp, c_pp, c_pp, c_void_p, c_int, c_int, c_int, c_float,

@@ -67,3 +67,22 @@ def set_dropout_trace(sink):
 def trace(kind, tag, value):
     if _trace is not None:
         _trace.append((kind, tag, value))
+
+
+# ------------------------------------------------------------------------------------------------ epsilon source
+# LunarisCoreVAE.forward draws its reparameterisation noise with torch.randn on the input's device. The golden
+# fixtures were produced by the reference on the CPU generator, whose stream differs from the CUDA generator's for
+# the same seed: parity tests install a source that returns the reference's exact draws. None in production.
+_eps_source = None
+
+
+def set_eps_source(fn):
+    """fn(batch, latent_dim, device) -> fp32 tensor [batch, latent_dim] on `device`, or None to restore torch.randn."""
+    global _eps_source
+    _eps_source = fn
+
+
+def draw_eps(batch, latent_dim, device):
+    if _eps_source is not None:
+        return _eps_source(batch, latent_dim, device).to(device=device, dtype=torch.float32).contiguous()
+    return torch.randn(batch, latent_dim, device=device, dtype=torch.float32)

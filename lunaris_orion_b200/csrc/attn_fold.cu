@@ -313,7 +313,10 @@ static int launch_fold(const bf16* y, const float* scale, const float* shift, co
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int smem = (2 * 32 + 8 + 2 * 8) * (C + 8) * 2 + 4 * 8 * 36 * 4 + 8 * 16 * 4 + 8 * 4 + 16;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the opt-in smem size is a per-device function attribute
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(attn_fold_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return LUN_E_ATTR;

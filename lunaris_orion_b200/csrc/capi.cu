@@ -94,6 +94,26 @@ int lun_convT4x4s2_bf16(const void* x, int B, int H, int W, int Cin, const void*
   return lun::launch_conv_fprop(x, B, H, W, w_packed, 16, g, bias, out, img_stats, static_cast<cudaStream_t>(stream));
 }
 
+int lun_head_linear_bf16(const void* x, int rows, int heads, int cin, const void* w, int cout, const float* bias,
+                         void* out, void* stream) {
+  // out[r, h*cout + n] = bias[h*cout + n] + sum_k x[r, h*cin + k] * w[h][n][k]: `heads` independent GEMMs in one launch.
+  // x is read as an NHWC tensor [rows, 1, heads, cin]: group h is the filter tap dx = h of a 1-pixel output grid.
+  if (heads < 1 || heads > lun::kMaxTaps) return LUN_E_TAPS;
+  lun::ConvGeom g{};
+  g.GB = rows; g.GH = 1; g.GW = 1;
+  g.in_mul = 1;
+  g.ntaps = 1;
+  g.nphase = heads;
+  g.grouped = 1;
+  for (int h = 0; h < heads; ++h) { g.dy[h] = 0; g.dx[h] = h; g.slab[h] = h; }
+  g.Cin = cin; g.Cout = cout;
+  g.block_n = cout >= 256 && cout % 256 == 0 ? 256 : cout >= 128 && cout % 128 == 0 ? 128 : cout % 64 == 0 ? 64 : 32;
+  g.OH = 1; g.OW = 1; g.o_mul = 1; g.o_ph = 0; g.o_pw = 0; g.ldo = heads * cout; g.o_coff = 0;
+  g.flags = bias ? LUN_EPI_BIAS : 0;
+  g.slope = 1.f;
+  return lun::launch_conv_fprop(x, rows, 1, heads, w, heads, g, bias, out, nullptr, static_cast<cudaStream_t>(stream));
+}
+
 int lun_wgrad_taps_bf16(const void* dy, int YB, int YH, int YW, int Cout, int dy_mul, int dy_ph, int dy_pw,
                         const void* x, int XB, int XH, int XW, int Cin, int in_mul, int GB, int GH, int GW,
                         int ntaps, const int* tdy, const int* tdx, const int* slab, float* dw, void* stream) {

@@ -18,6 +18,7 @@
 #include "ptx.cuh"
 #include "launch_count.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace lun {
 
@@ -25,6 +26,7 @@ constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kAReuseBox = 130 * 128;   // 130 pixel rows (one halo pixel on each side) x 64 bf16
 constexpr int kAReuseSlot = 17 * 1024;  // rounded up so the weight tiles behind it stay 1024-byte aligned
+constexpr int kBiasSmem = 2048;         // bias entries staged in shared memory
 
 struct __align__(16) PipeBars {
   uint64_t full[8];
@@ -38,7 +40,8 @@ struct __align__(16) PipeBars {
 // CG = 1: one CTA per 128-pixel tile. CG = 2: a CTA pair (cluster of 2) computes a 256-pixel x block_n tile with
 // tcgen05.mma.cta_group::2 - each CTA loads its own 128 pixel rows of A and HALF of the weight tile, the leader CTA
 // issues the MMAs, both CTAs drain their own 128 accumulator rows.
-template <int CG>
+// STATS: instantiation with the statistics epilogue (its register accumulators cost the plain instantiation nothing).
+template <int CG, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const ConvGeom g, const float* __restrict__ bias, void* __restrict__ out,
@@ -54,10 +57,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int stage_tx = (g.a_reuse ? kAReuseBox : kABytes) + taps_per_stage * b_bytes;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const int stages = g.stages;
-  uint8_t* s_stage = smem + stages * stage_bytes;  // 2 x 8 KB output staging tiles (128 rows x 64 B, 64B swizzle)
-  PipeBars* bars = reinterpret_cast<PipeBars*>(s_stage + kABytes);
+  // output staging: per epilogue WARP, stg_bufs (1 or 2) sub-tiles of 2 KB (32 rows x 64 B, 64B swizzle); then, with
+  // EPI_STATS, 8 KB of warp-private column-sum slots [8 warps][4 chunks][16 column pairs] x float4
+  uint8_t* s_stage = smem + stages * stage_bytes;
+  const int nbuf = g.stg_bufs;
+  float* s_cstat = reinterpret_cast<float*>(s_stage + 8 * nbuf * 2048);
+  PipeBars* bars = reinterpret_cast<PipeBars*>(s_stage + 8 * nbuf * 2048 + ((g.flags & EPI_STATS) ? 8192 : 0));
   float* s_bias = reinterpret_cast<float*>(bars + 1);   // [Cout]
-  float* s_stats = s_bias + g.Cout;                     // [2 * Cout] when EPI_STATS
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,10 +93,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < g.Cout; i += kThreads) s_bias[i] = (g.flags & EPI_BIAS) ? bias[i] : 0.f;
-  if (g.flags & EPI_STATS) {
-    for (int i = threadIdx.x; i < 2 * g.Cout; i += kThreads) s_stats[i] = 0.f;
-  }
+  // grouped mode: phase p is an independent GEMM group writing channels [p * Cout, (p + 1) * Cout) of the output
+  // (bias vectors longer than kBiasSmem entries - the 32768-wide decoder fc - are read from global memory instead)
+  const int nbias = g.grouped ? g.Cout * nphase : g.Cout;
+  const bool bias_smem = nbias <= kBiasSmem;
+  if (bias_smem)
+    for (int i = threadIdx.x; i < nbias; i += kThreads) s_bias[i] = (g.flags & EPI_BIAS) ? bias[i] : 0.f;
   if (warp == 1) {
     if (CG == 2) {
       tmem_alloc_pair(&bars->tmem_base, tmem_cols);
@@ -187,29 +195,70 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     // Two warps share each TMEM lane quarter and split the accumulator columns (half 0: first chunks, half 1: the
-    // rest), so a 128x256 tile is drained by 8 warps; each half owns an 8 KB staging tile (128 rows x 32 channels,
-    // 64-byte swizzle) that leaves through its own TMA store. TMEM loads are software-pipelined one chunk ahead.
+    // rest), so a 128x256 tile is drained by 8 warps. Every warp is self-contained: it stages its own 32 rows x 32
+    // channels (2 KB, 64-byte swizzle) in private shared memory and sends them off with its own TMA store, so the
+    // epilogue has no CTA-level or half-level barriers at all (a chunk used to cost two 128-thread rendezvous, which
+    // bounded the 1x1 and thin-K convolutions). TMEM loads are software-pipelined one chunk ahead.
     const int ew = warp - 2;
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = ew >> 2;
     const int row = q * 32 + lane;      // accumulator row == pixel index inside the tile
-    const bool do_stats = g.flags & EPI_STATS, out_f32 = g.flags & EPI_OUT_F32, tma_out = g.flags & EPI_TMA_STORE;
+    const bool do_stats = STATS && (g.flags & EPI_STATS);
+    const bool out_f32 = g.flags & EPI_OUT_F32, tma_out = g.flags & EPI_TMA_STORE;
     const bool stats_img = g.flags & EPI_STATS_IMG;
     const bool col_stats = (g.flags & EPI_COL_STATS) && tma_out;   // sums read back from the staged tile
+    const bool drop_sum = g.flags & EPI_DROP_SUM;
     const float slope = (g.flags & EPI_LEAKY) ? g.slope : 1.f;
-    const bool half_leader = (threadIdx.x == 64 + half * 128);
-    const uint32_t stg_base = smem_u32(s_stage) + half * 8192;
-    const uint32_t stg_row = stg_base + row * 64;
+    const uint32_t stg_warp = smem_u32(s_stage) + ew * nbuf * 2048;
     const int nchunks = block_n >> 5;
     const int ch_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
     const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
-    const int bar_a = 1 + 2 * half, bar_b = 2 + 2 * half;
+    const int nch = ch_hi - ch_lo;      // <= 4 (block_n <= 256)
+    // this warp's 32 rows inside the tile, as an offset of its TMA store box (box = {32 ch, sub_w, sub_h, sub_b})
+    const int sub_w0 = (q * 32) % g.TW, sub_h0 = ((q * 32) / g.TW) % g.TH, sub_b0 = (q * 32) / (g.TW * g.TH);
+    // Column statistics (col_stats): after a chunk is staged the warp re-reads its bf16 sub-tile (what was stored):
+    // lane (cp = lane & 15, rh = lane >> 4) owns the column PAIR {2 cp, 2 cp + 1} of rows 2 i + rh - sixteen conflict-
+    // free 32-bit loads. The two row halves are combined by one shuffle and added to a warp-private shared-memory slot
+    // (plain read-modify-write: no ATOMS.CAST.SPIN loops), which lives across tiles - a CTA keeps its channel block
+    // while item_stride % n_blocks == 0 - and is flushed with global reductions when the channel block (or, for
+    // per-image statistics, the image) changes and at the end.
+    const int cp = lane & 15, rh = lane >> 4;
+    float4* cs_slot = reinterpret_cast<float4*>(s_cstat) + (ew * 4) * 16 + cp;    // + ci * 16
+    if (do_stats && col_stats && lane < 16) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) cs_slot[ci * 16] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    int acc_blk = -1, acc_img = 0;      // channel block / image the slot sums belong to
+    auto flush_stats = [&]() {
+      if (acc_blk < 0) return;
+      __syncwarp();
+      if (lane < 16) {
+        float* base = stats + (stats_img ? static_cast<size_t>(acc_img) * 2 * g.Cout : 0) + acc_blk * block_n + 2 * cp;
+        for (int ci = 0; ci < nch; ++ci) {
+          const float4 t = cs_slot[ci * 16];
+          float* d = base + (ch_lo + ci) * 32;
+          atomicAdd(d, t.x);
+          atomicAdd(d + 1, t.y);
+          if (!drop_sum) {
+            atomicAdd(d + g.Cout, t.z);
+            atomicAdd(d + g.Cout + 1, t.w);
+          }
+          cs_slot[ci * 16] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      __syncwarp();
+    };
+    // drop_key(seed, idx8) for idx8 < 2^30: seed_lo ^ (idx8 * 4) ^ seed_hi * 0x85EBCA6B
+    const uint32_t drop_k0 = static_cast<uint32_t>(g.drop_seed) ^ static_cast<uint32_t>(g.drop_seed >> 32) * 0x85EBCA6BU;
     int acc = 0;
     uint32_t pacc = 0;
-    bool store_pending = false;
+    int stores_issued = 0;              // TMA stores committed by this warp so far (staging ring position)
     for (int tile = first_item; tile < total_tiles; tile += item_stride) {
       const int phase = tile / tiles_pp, tl = tile % tiles_pp;
-      const int o_ph = nphase > 1 ? phase >> 1 : g.o_ph, o_pw = nphase > 1 ? phase & 1 : g.o_pw;
+      const bool spatial_phase = nphase > 1 && !g.grouped;       // transposed conv: phase = output (row, col) parity
+      const int o_ph = spatial_phase ? phase >> 1 : g.o_ph, o_pw = spatial_phase ? phase & 1 : g.o_pw;
+      const int cbase = g.grouped ? phase * g.Cout : 0;          // grouped GEMM: phase = output channel group
       const int n_blk = tl % n_blocks;
       int m = (tl / n_blocks) * CG + cta_rank;
       const int tw = m % g.ntw;
@@ -222,7 +271,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int rows_left = (g.GB - tb * g.TB) * g.TW * g.TH;     // rows of this tile that lie inside the batch
       const int nvalid = rows_left < 128 ? rows_left : 128;
       const size_t pix = (static_cast<size_t>(gb) * g.OH + (gh * g.o_mul + o_ph)) * g.OW + (gw * g.o_mul + o_pw);
-      const size_t obase = pix * g.ldo + g.o_coff + n_blk * block_n;
+      const size_t obase = pix * g.ldo + g.o_coff + cbase + n_blk * block_n;
+      if (do_stats && col_stats && (n_blk != acc_blk || (stats_img && tb != acc_img))) {
+        flush_stats();
+        acc_blk = n_blk;
+        acc_img = tb;
+      }
 
       mbar_wait(&bars->tfull[acc], pacc);
       tc_fence_after();
@@ -230,11 +284,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // process one 32-column chunk held in registers `r` (bias, activation, store, statistics)
       auto process = [&](uint32_t (&r)[32], int ch) {
         const int c0 = ch << 5;
-        const int nb = n_blk * block_n + c0;
+        const int nb = cbase + n_blk * block_n + c0;
         float bv[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 t = *reinterpret_cast<const float4*>(s_bias + nb + 4 * j);
+          const float4 t = bias_smem ? *reinterpret_cast<const float4*>(s_bias + nb + 4 * j)
+                           : (g.flags & EPI_BIAS) ? __ldg(reinterpret_cast<const float4*>(bias + nb) + j)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
         }
         float v[32];
@@ -254,29 +310,76 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           if (tma_out) {
-            // the staging tile is reused: wait until the previous TMA store has finished reading it
-            if (store_pending) {
-              if (half_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");
+            const uint32_t stg_base = stg_warp + (nbuf == 2 ? (stores_issued & 1) * 2048 : 0);
+            // the staging tile is reused: wait until the TMA store that last read it has finished with it
+            if (stores_issued >= nbuf) {
+              if (lane == 0) {
+                if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              __syncwarp();
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t chunk = static_cast<uint32_t>(j ^ ((row >> 1) & 3));
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + (chunk << 4)), "r"(p[4 * j]),
-                           "r"(p[4 * j + 1]), "r"(p[4 * j + 2]), "r"(p[4 * j + 3])
+              const uint32_t chunk = static_cast<uint32_t>(j ^ ((lane >> 1) & 3));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + lane * 64 + (chunk << 4)),
+                           "r"(p[4 * j]), "r"(p[4 * j + 1]), "r"(p[4 * j + 2]), "r"(p[4 * j + 3])
                            : "memory");
             }
             fence_proxy_async();
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");
-            if (half_leader) {
+            __syncwarp();
+            if (lane == 0) {
               asm volatile(
                   "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                       &tmO),
-                  "r"(stg_base), "r"(g.o_coff + nb), "r"(tw * g.TW), "r"(th * g.TH), "r"(tb * g.TB)
+                  "r"(stg_base), "r"(g.o_coff + nb), "r"(tw * g.TW + sub_w0), "r"(th * g.TH + sub_h0),
+                  "r"(tb * g.TB + sub_b0)
                   : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            store_pending = true;
+            ++stores_issued;
+            if (do_stats && col_stats) {
+              // column-pair sums from the staged bf16 sub-tile (valid until this warp's next wait on the buffer; the
+              // TMA store only reads it). Word (row, pair cp) sits in 16-byte chunk (cp >> 2) ^ ((row >> 1) & 3)
+              // = (cp >> 2) ^ (i & 3) of the 64-byte row 2 i + rh.
+              const uint32_t colw = stg_base + rh * 64 + (cp & 3) * 4;
+              const uint32_t cj = static_cast<uint32_t>(cp) >> 2;
+              const int left = nvalid - q * 32 - rh;         // valid rows: 2 i < left
+              float a10 = 0.f, a11 = 0.f, a20 = 0.f, a21 = 0.f;
+              // replay of the elementwise dropout on the stored tensor (EPI_DROP_SUM): element index e = pixel * ldo +
+              // channel (32-bit, tile = 128 consecutive pixels - checked by the launcher); e is even for the low column
+              // of the pair, so both columns share one hash word (same stream as drop_keep1())
+              const uint32_t e_row0 =
+                  static_cast<uint32_t>((static_cast<size_t>(tb) * g.OH + th) * g.OW + tw * 128 + q * 32 + rh) *
+                      static_cast<uint32_t>(g.ldo) + static_cast<uint32_t>(g.o_coff + nb + 2 * cp);
+#pragma unroll 8
+              for (int i = 0; i < 16; ++i) {
+                uint32_t w;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(colw + i * 128 + ((cj ^ (i & 3)) << 4)) : "memory");
+                float f0 = 2 * i < left ? __uint_as_float(w << 16) : 0.f;
+                float f1 = 2 * i < left ? __uint_as_float(w & 0xffff0000u) : 0.f;
+                if (drop_sum) {
+                  const uint32_t e = e_row0 + static_cast<uint32_t>(2 * i) * static_cast<uint32_t>(g.ldo);
+                  const uint32_t h = hash32((drop_k0 ^ ((e >> 3) << 2)) + ((e >> 1) & 3u));
+                  f0 = (h & 0xFFFFu) >= g.drop_thresh16 ? rbf(f0 * g.drop_scale) : 0.f;
+                  f1 = (h >> 16) >= g.drop_thresh16 ? rbf(f1 * g.drop_scale) : 0.f;
+                }
+                a10 += f0;
+                a11 += f1;
+                a20 = fmaf(f0, f0, a20);
+                a21 = fmaf(f1, f1, a21);
+              }
+              a10 += __shfl_xor_sync(0xffffffffu, a10, 16);
+              a11 += __shfl_xor_sync(0xffffffffu, a11, 16);
+              a20 += __shfl_xor_sync(0xffffffffu, a20, 16);
+              a21 += __shfl_xor_sync(0xffffffffu, a21, 16);
+              if (rh == 0) {
+                float4* slot = cs_slot + (ch - ch_lo) * 16;
+                float4 t = *slot;
+                t.x += a10; t.y += a11; t.z += a20; t.w += a21;
+                *slot = t;
+              }
+            }
           } else if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + obase + c0);
 #pragma unroll
@@ -290,52 +393,6 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               v[2 * j + 1] = __uint_as_float(p[j] & 0xffff0000u);
             }
           }
-        }
-        if (do_stats && col_stats) {
-          // Column sums straight from the staged bf16 tile (what was stored): this thread owns column `lane` of the 32
-          // rows [32*rg, 32*rg+32). A warp reads one 64-byte row per load (conflict-free), and the 62-shuffle
-          // transpose-reduce of the register path is gone. The tile stays valid until the bar_b rendezvous that
-          // precedes the next chunk's writes (the TMA store only reads it).
-          const int rg = ew & 3;
-          const uint32_t col = stg_base + rg * 2048 + (lane & 7) * 2;
-          const uint32_t cj = static_cast<uint32_t>(lane) >> 3;
-          const uint32_t o0 = col + (cj << 4), o1 = col + ((cj ^ 1u) << 4), o2 = col + ((cj ^ 2u) << 4),
-                         o3 = col + ((cj ^ 3u) << 4);
-          const int left = nvalid - rg * 32;           // valid rows of this group (a ragged last batch tile)
-          float a1 = 0.f, a2 = 0.f;
-          const bool drop_sum = g.flags & EPI_DROP_SUM;
-          // drop_key(seed, idx8) for idx8 < 2^30: seed_lo ^ (idx8 * 4) ^ seed_hi * 0x85EBCA6B
-          const uint32_t drop_k0 = static_cast<uint32_t>(g.drop_seed) ^ static_cast<uint32_t>(g.drop_seed >> 32) * 0x85EBCA6BU;
-          const uint32_t e_row0 =
-              static_cast<uint32_t>((static_cast<size_t>(tb) * g.OH + th) * g.OW + tw * 128 + rg * 32) *
-                  static_cast<uint32_t>(g.ldo) + static_cast<uint32_t>(g.o_coff + nb + lane);
-#pragma unroll 1
-          for (int i0 = 0; i0 < 32; i0 += 8) {
-            uint16_t hv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int sw = (u >> 1) & 3;             // == (row >> 1) & 3: 32*rg + i0 is a multiple of 8
-              const uint32_t addr = (sw == 0 ? o0 : sw == 1 ? o1 : sw == 2 ? o2 : o3) + (i0 + u) * 64;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv[u]) : "r"(addr) : "memory");
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              float f = i0 + u < left ? __uint_as_float(static_cast<uint32_t>(hv[u]) << 16) : 0.f;
-              if (drop_sum) {
-                // replay of the elementwise dropout on the stored tensor: element index e = pixel * ldo + channel
-                // (32-bit, tile = 128 consecutive pixels - checked by the launcher); same stream as drop_keep1()
-                const uint32_t e = e_row0 + static_cast<uint32_t>(i0 + u) * static_cast<uint32_t>(g.ldo);
-                const uint32_t h = hash32((drop_k0 ^ ((e >> 3) << 2)) + ((e >> 1) & 3u));
-                const uint32_t k16 = (e & 1u) ? (h >> 16) : (h & 0xFFFFu);
-                f = k16 >= g.drop_thresh16 ? rbf(f * g.drop_scale) : 0.f;
-              }
-              a1 += f;
-              a2 = fmaf(f, f, a2);
-            }
-          }
-          float* dst = stats_img ? stats + static_cast<size_t>(tb) * 2 * g.Cout + nb + lane : &s_stats[nb + lane];
-          atomicAdd(dst, a1);
-          atomicAdd(dst + g.Cout, a2);
         }
         if (do_stats && !col_stats) {
           float s1[32], s2[32];
@@ -358,15 +415,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
             }
           }
-          if (stats_img) {
-            // GroupNorm: the tile lies inside image tb; one coalesced reduction per warp straight to global
-            float* st = stats + static_cast<size_t>(tb) * 2 * g.Cout + nb + lane;
-            atomicAdd(st, s1[0]);
-            atomicAdd(st + g.Cout, s2[0]);
-          } else {
-            atomicAdd(&s_stats[nb + lane], s1[0]);
-            atomicAdd(&s_stats[g.Cout + nb + lane], s2[0]);
-          }
+          // one coalesced reduction per warp straight to global (per image for GroupNorm)
+          float* st = stats + (stats_img ? static_cast<size_t>(tb) * 2 * g.Cout : 0) + nb + lane;
+          atomicAdd(st, s1[0]);
+          atomicAdd(st + g.Cout, s2[0]);
         }
       };
       uint32_t ra[32], rb[32];
@@ -390,11 +442,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
-    if (store_pending && half_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (do_stats && !stats_img) {
-      asm volatile("bar.sync 5, 256;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < 2 * g.Cout; i += 256) atomicAdd(stats + i, s_stats[i]);
-    }
+    if (do_stats && col_stats) flush_stats();
+    if (stores_issued && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -459,13 +508,12 @@ int make_tmap_2d(CUtensorMap* m, const void* base, long rows, long cols, int box
 }
 
 int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
@@ -493,6 +541,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   if (g.TW * g.in_mul > 256 || g.TH * g.in_mul > 256 || g.TB > 256) return 5;
   if (g.Cout > 2048 && (g.flags & EPI_STATS)) return 6;
   if ((g.flags & EPI_STATS_IMG) && (!(g.flags & EPI_STATS) || g.TB != 1)) return 6;
+  if (g.grouped && ((g.flags & EPI_STATS) || g.nphase < 2)) return 6;
   if ((g.flags & EPI_DROP_SUM) &&
       (!(g.flags & EPI_STATS) || (g.flags & (EPI_OUT_F32 | EPI_STATS_IMG)) || g.o_mul != 1 || g.TW != 128 || g.TH != 1 ||
        g.TB != 1 || (double)g.GB * g.OH * g.OW * g.ldo >= 4294967296.0))
@@ -554,26 +603,52 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
   rc = make_tmap_2d(&tmB, wpk, (long)nslabs * g.Cout, g.Cin, g.block_n / cg);
   if (rc) return rc;
   if (g.flags & EPI_TMA_STORE) {
-    rc = make_tmap_nhwc_ex(&tmO, out, g.GB, g.OH, g.OW, g.ldo, 32, g.TW, g.TH, g.TB, 1, CU_TENSOR_MAP_SWIZZLE_64B);
+    // one store per epilogue warp: its 32 accumulator rows = a {32 ch, sub_w, sub_h, sub_b} box of the output tensor
+    const int sub_w = g.TW < 32 ? g.TW : 32;
+    const int sub_h = g.TH < 32 / sub_w ? g.TH : 32 / sub_w;
+    const int sub_b = 32 / (sub_w * sub_h);
+    if (sub_b > g.TB) return 5;
+    rc = make_tmap_nhwc_ex(&tmO, out, g.GB, g.OH, g.OW, g.ldo, 32, sub_w, sub_h, sub_b, 1, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   } else {
     tmO = tmA;
   }
   const int stage_bytes = g.a_reuse ? kAReuseSlot + 3 * (g.block_n / cg * 128) : kABytes + g.block_n / cg * 128;
-  const int extra = kABytes + (int)sizeof(PipeBars) + g.Cout * 4 + ((g.flags & EPI_STATS) ? 2 * g.Cout * 4 : 0) + 1024;
-  int stages = (227 * 1024 - extra) / stage_bytes;
-  if (stages > 8) stages = 8;
+  // two staging tiles per epilogue half (the next chunk is written while the previous TMA store drains) whenever the
+  // operand ring keeps at least 4 stages; the 65 KB stages of the A-reuse configuration leave room for one
+  static int stg_mode = -1;
+  if (stg_mode < 0) {
+    const char* e = getenv("LUN_CONV_STG2");
+    stg_mode = e ? atoi(e) : 1;
+  }
+  int stages = 0, extra = 0;
+  for (g.stg_bufs = (stg_mode && (g.flags & EPI_TMA_STORE)) ? 2 : 1; g.stg_bufs >= 1; --g.stg_bufs) {
+    extra = 8 * g.stg_bufs * 2048 + ((g.flags & EPI_STATS) ? 8192 : 0) + (int)sizeof(PipeBars) +
+            (g.Cout * (g.grouped ? g.nphase : 1) <= kBiasSmem ? g.Cout * (g.grouped ? g.nphase : 1) * 4 : 0) + 1024;
+    stages = (227 * 1024 - extra) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages >= 4 || g.stg_bufs == 1 || stg_mode == 2) break;
+  }
+  if (stages < 1) return 5;
   g.stages = stages;
   const int smem_bytes = stages * stage_bytes + extra;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(conv_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess)
-      return 8;
-    configured = true;
+  // the opt-in shared-memory size is a per-device function attribute: set it once for every device this process uses
+  {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 8;
+    if (!configured[dev]) {
+      const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+      if (cudaFuncSetAttribute(conv_fprop_kernel<1, false>, attr, 227 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_fprop_kernel<1, true>, attr, 227 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_fprop_kernel<2, false>, attr, 227 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_fprop_kernel<2, true>, attr, 227 * 1024) != cudaSuccess)
+        return 8;
+      configured[dev] = true;
+    }
   }
+  const bool with_stats = g.flags & EPI_STATS;
   const int total_items = m_tiles / cg * (g.Cout / g.block_n) * g.nphase;
   int grid = sms;
   if (grid > total_items * cg) grid = total_items * cg;
@@ -590,9 +665,14 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, conv_fprop_kernel<2>, tmA, tmA2, tmB, tmO, g, bias, out, stats) != cudaSuccess) return 9;
+    const cudaError_t e = with_stats
+        ? cudaLaunchKernelEx(&cfg, conv_fprop_kernel<2, true>, tmA, tmA2, tmB, tmO, g, bias, out, stats)
+        : cudaLaunchKernelEx(&cfg, conv_fprop_kernel<2, false>, tmA, tmA2, tmB, tmO, g, bias, out, stats);
+    if (e != cudaSuccess) return 9;
+  } else if (with_stats) {
+    conv_fprop_kernel<1, true><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmO, g, bias, out, stats);
   } else {
-    conv_fprop_kernel<1><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmO, g, bias, out, stats);
+    conv_fprop_kernel<1, false><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmO, g, bias, out, stats);
   }
   note_launch(1);
   return cudaGetLastError() == cudaSuccess ? 0 : 9;

@@ -34,6 +34,7 @@ struct ConvGeom {
   int dy[kMaxTaps], dx[kMaxTaps], slab[kMaxTaps];
   int Cin, Cout, block_n;
   int stages;
+  int stg_bufs;        // (set by the launcher) output staging tiles per epilogue half: 1 or 2
   // A-tile reuse across the dx taps of a filter row (3 consecutive taps with equal dy and dx, dx+1, dx+2, full-width
   // row tiles): one TW+2-pixel A box per (dy, channel chunk) feeds three MMA groups through descriptor row offsets.
   int a_reuse;
@@ -44,6 +45,9 @@ struct ConvGeom {
   // nphase > 1 (transposed conv, all output phases in ONE launch): the tap list holds nphase runs of ntaps taps; a work
   // item is (phase, pixel tile, channel block) and phase p writes output phase (o_ph, o_pw) = (p >> 1, p & 1)
   int nphase;
+  // grouped != 0 (with nphase > 1): the phases are independent GEMM groups instead - phase p uses taps
+  // [p * ntaps, (p + 1) * ntaps) and writes output channels o_coff + p * Cout + n (bias index p * Cout + n)
+  int grouped;
   // EPI_DROP_SUM: the elementwise dropout this sum replays (seed, 16-bit drop threshold, bf16 1/(1-p))
   unsigned long long drop_seed;
   unsigned int drop_thresh16;
@@ -61,7 +65,8 @@ struct WgradGeom {
   int Cin, Cout;       // Cout = GEMM M (blocks of 128), Cin = GEMM N (blocks of block_n)
   int block_n;
   int stages;
-  int splits;          // split-K factor (k-chunks are dealt round-robin to splits)
+  int splits;          // split-K factor: split s covers k-chunks [chunks * s / splits, chunks * (s + 1) / splits)
+  int lockstep, nsub;  // lockstep schedule: worker w owns tile w % tiles and splits (w / tiles) * nsub + [0, nsub)
   int dy_mul, dy_ph, dy_pw;  // dY pixel = grid*dy_mul + phase  (transposed-conv phases)
   // reuse3: the three dx taps of a filter row share one (TW+2)-pixel X box; a unit accumulates 3 tiles (one per tap)
   int reuse3;

@@ -4,8 +4,13 @@
 // a TMA box of {64 channels, 64 pixels} lands in shared memory as 64 rows of 128 bytes (128-byte swizzle), which is
 // exactly the canonical MN-major SWIZZLE_128B UMMA layout (LBO = 8 KB between 64-channel atoms, SBO = 1 KB between
 // 8-pixel groups). tcgen05.mma M=128 (Cout block), N=block_n (Cin block), K=16 pixels, fp32 accumulators in TMEM.
-// Work unit = (Cout block, Cin block, tap, K-split); units are dealt round-robin to a persistent grid and each
-// finishes with vectorised fp32 red.global.add into the packed gradient buffer (zeroed by the caller).
+// Work unit = (Cout block, Cin block, tap, K-split); each finishes with vectorised fp32 red.global.add into the packed
+// gradient buffer (zeroed by the caller). Two schedules:
+//   lockstep (tiles <= workers): a worker owns ONE output tile and a contiguous 1/wpt of the pixel range, walked as
+//     nsub consecutive sub-units (the drain of one overlaps the main loop of the next). All workers of a K slice move
+//     through the same pixels at the same time, so every dY / X byte comes from DRAM once and from L2 for the other
+//     tiles (round-robin units straddled slices and re-fetched each of them about twice: 4.8 GB read for 2.15 GB);
+//   round-robin (more tiles than workers): units dealt to a persistent grid.
 //
 // Replaces the autograd weight-gradients of the reference's conv2d / conv_transpose2d call sites
 // (lunar_evaluator.py:249,134,255; lunar_generate.py:36,41,95-116,169-187).
@@ -68,9 +73,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 
   const int m_blocks = (g.Cout + 128 * CG - 1) / (128 * CG);
   const int n_blocks = (g.Cin + block_n - 1) / block_n;
-  const int first_unit = blockIdx.x / CG, unit_stride = gridDim.x / CG;
+  const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
   const int tiles = m_blocks * n_blocks * (g.ntaps / tps);
   const int units = tiles * g.splits;
+  // k-th unit of this worker -> (K split, tile)
+  auto unit_of = [&](int k, int& split, int& t) -> bool {
+    if (g.lockstep) {
+      if (k >= g.nsub) return false;
+      t = worker % tiles;
+      split = (worker / tiles) * g.nsub + k;
+      return true;
+    }
+    const int u = worker + k * nworkers;
+    if (u >= units) return false;
+    split = u / tiles;
+    t = u % tiles;
+    return true;
+  };
   const int chunks = g.ntb * g.nth * g.ntw;  // 64-pixel k-chunks
   const int acc_cols = r3 ? 3 * block_n : 2 * block_n;
   const uint32_t tmem_cols = acc_cols <= 64 ? 64u : acc_cols <= 128 ? 128u : acc_cols <= 256 ? 256u : 512u;
@@ -111,9 +130,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     // the 2 + block_n/64 loads of a stage are issued in parallel instead of back to back by one thread.
     int s = 0;
     uint32_t ph = 0;
-    for (int u = first_unit; u < units; u += unit_stride) {
-      const int split = u / tiles;
-      int t = u % tiles;
+    int split, t;
+    for (int k = 0; unit_of(k, split, t); ++k) {
       const int m_blk = t % m_blocks;
       t /= m_blocks;
       const int n_blk = t % n_blocks;
@@ -152,8 +170,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     uint32_t ph = 0;
     int acc = 0;
     uint32_t pacc = 0;
-    for (int u = first_unit; cta_rank == 0 && u < units; u += unit_stride) {
-      const int split = u / tiles;
+    int split, t;
+    for (int k = 0; cta_rank == 0 && unit_of(k, split, t); ++k) {
       const int nk = chunk_lo(split + 1) - chunk_lo(split);
       if (nk == 0) continue;
       mbar_wait(&bars->tempty[acc], pacc ^ 1);
@@ -196,11 +214,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t pacc = 0;
-    for (int u = first_unit; u < units; u += unit_stride) {
-      const int split = u / tiles;
+    int split, t;
+    for (int k = 0; unit_of(k, split, t); ++k) {
       const int nk = chunk_lo(split + 1) - chunk_lo(split);
       if (nk == 0) continue;
-      int t = u % tiles;
       const int m_blk = t % m_blocks;
       t /= m_blocks;
       const int n_blk = t % n_blocks;
@@ -324,7 +341,10 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
   if (stages > 8) stages = 8;
   g.stages = stages;
   const int smem_bytes = stages * stage_bytes + extra;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the opt-in smem size is a per-device function attribute
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
             cudaSuccess ||
@@ -349,6 +369,26 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
   g.splits = splits;
   int grid = workers;
   if (grid > tiles * splits) grid = tiles * splits;
+  static int lock_mode = -1;
+  if (lock_mode < 0) {
+    const char* e = getenv("LUN_WGRAD_LOCKSTEP");
+    lock_mode = e ? atoi(e) : 1;
+  }
+  g.lockstep = 0;
+  g.nsub = 1;
+  if (lock_mode && tiles <= workers) {
+    int wpt = workers / tiles;                      // workers per output tile = major K slices
+    if (wpt > chunks / 8) wpt = chunks / 8;         // keep at least 8 k-chunks per unit
+    if (wpt >= 1 && tiles * wpt * 10 >= workers * 9) {      // at most 10 % of the grid may stay idle
+      int nsub = chunks / wpt / 512;                // sub-units of ~512 chunks: the drain overlaps the next main loop
+      if (nsub < 1) nsub = 1;
+      if (nsub > 16) nsub = 16;
+      g.lockstep = 1;
+      g.nsub = nsub;
+      g.splits = wpt * nsub;
+      grid = tiles * wpt;
+    }
+  }
   grid *= cg;
   if (cg == 2) {
     cudaLaunchConfig_t cfg{};

@@ -307,7 +307,10 @@ int lun_convT4x4s2_halo_bf16(const void* x, int B, int H, int W, int Cin, const 
   g.stages = stages;
   g.flags = (bias ? EPI_BIAS : 0) | (img_stats ? (EPI_STATS | EPI_STATS_IMG) : 0);
   const int smem = w_bytes + stages * kCtHaloSlot + (int)sizeof(CtBars) + Cout * 4 + 1024;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the opt-in smem size is a per-device function attribute
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(convt_halo_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
             cudaSuccess ||

@@ -381,7 +381,10 @@ int lun_flash_attn2d_dqk_bf16(const void* qk, const void* v, const void* dy, con
   if (ycst > kFbMaxYc) ycst = kFbMaxYc;
   if (ycst < 2) return LUN_E_SHAPE;
   const int smem = (1 + nbuf + 2 + nch + ycst) * kFbTile + (int)sizeof(FbBars) + 1024;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the opt-in smem size is a per-device function attribute
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(flash_attn2d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess)

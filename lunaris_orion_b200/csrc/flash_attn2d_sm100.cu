@@ -413,7 +413,10 @@ static int launch_flash(const void* qk, const void* v, const void* x, void* y, c
   const int vatoms = vw / 64 / cg;
   const int smem = kFaTileBytes + kFaKStages(cg) * (kFaTileBytes / cg) + kFaPStages(cg) * 2 * kFaTileBytes + 2 * vatoms * kFaTileBytes +
                    (int)sizeof(FaBars) + 1024;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the opt-in smem size is a per-device function attribute
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(flash_attn2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
             cudaSuccess ||

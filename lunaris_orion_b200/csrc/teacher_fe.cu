@@ -270,7 +270,10 @@ int lun_fe_branches(const void* y0, const float* scale, const float* shift, cons
     wt.dw_w[i] = dw_w[i]; wt.dw_b[i] = dw_b[i]; wt.pw_w[i] = pw_w[i]; wt.pw_b[i] = pw_b[i];
   }
   const int smem = (32 * kPlane + 3 * 32 * 40 + 96 + 192) * (int)sizeof(float) + (3 * 64 + 256) * kDPitch;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the opt-in smem size is a per-device function attribute
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(fe_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return LUN_E_ATTR;

@@ -183,25 +183,15 @@ class LunarMoETeacher(nn.Module):
             _warn_once("LunarMoETeacher.forward in eval mode returns outputs without an autograd graph "
                        "(the reference would back-propagate through them); wrap the call in torch.no_grad().")
         B, _, H, W = x.shape
-        hw = float(H * W)
         params = _trunk_grad_params(self) if grad_on else []
         res = _TeacherTrunk.apply(self, x.detach(), grad_on, *params)
-        pooled_fe, pooled = res[0], res[1:1 + self.num_experts]
-        fmaps = res[1 + self.num_experts:]
-
-        with torch.autocast("cuda", enabled=False), torch.set_grad_enabled(grad_on):
-            weights = torch.softmax(_mlp_head(self.gate, pooled_fe / hw, False, self.training, "gate_drop"), dim=1)
-            means = [p / hw for p in pooled]
-            quals = [_mlp_head(self.quality_heads[e], means[e], True, self.training, f"quality_drop.{e}")
-                     for e in range(self.num_experts)]
-            wq = (torch.stack(quals, 1) * weights.unsqueeze(-1)).sum(1)
-            comb = (torch.stack(means, 1) * weights.unsqueeze(-1)).sum(1)
-            style = _mlp_head(self.style_net, comb, True, self.training, "style_drop")
-            prompt = _mlp_head(self.prompt_net, comb, True, self.training, "prompt_drop")
-            sem = torch.sigmoid(_mlp_head(self.semantic_head, means[0], True, self.training, "semantic_drop"))
-            sem = sem * F.cosine_similarity(prompt, prompt.detach(), dim=1).unsqueeze(1)
+        pooled_fe, pooled = res[0], res[1]                    # channel sums: [B,128] and [E,B,C]
+        fmaps = res[2:]
+        hp = _head_params(self)
+        quality, weights, style, prompt, sem = _HeadsFn.apply(self, 1.0 / float(H * W), grad_on, pooled_fe, pooled,
+                                                              *(hp if grad_on else []))
         return {
-            'quality_scores': torch.sigmoid(wq),
+            'quality_scores': quality,
             'expert_weights': weights,
             'style_embedding': style,
             'prompt_embedding': prompt,
@@ -210,22 +200,122 @@ class LunarMoETeacher(nn.Module):
         }
 
 
-def _mlp_head(seq, pooled, ln, training, tag):
-    """[LayerNorm] -> Linear -> LeakyReLU -> Dropout -> Linear of a head's nn.Sequential on pooled [B,C] features
-    (lunar_evaluator.py:353-397; module indices: gate 2,5 - the others 2,3,6). The Dropout keep-mask is drawn
-    explicitly (and offered to the dropout trace) instead of through nn.Dropout."""
-    if ln:
-        h = F.layer_norm(pooled, pooled.shape[-1:], seq[2].weight, seq[2].bias, seq[2].eps)
-        l1, drop, l2 = seq[3], seq[5], seq[6]
-    else:
-        h = pooled
-        l1, drop, l2 = seq[2], seq[4], seq[5]
-    h = F.leaky_relu(F.linear(h, l1.weight, l1.bias), _SLOPE)
-    if training and drop.p > 0:
-        keep = torch.empty_like(h).bernoulli_(1.0 - drop.p).mul_(1.0 / (1.0 - drop.p))
-        _host.trace("mask", tag, keep)
-        h = h * keep
-    return F.linear(h, l2.weight, l2.bias)
+_HEAD_TAGS = ("gate_drop", "quality_drop.{e}", "semantic_drop", "style_drop", "prompt_drop")
+
+
+def _head_modules(teacher):
+    """Heads in the order of the C ABI (include/lunaris_b200.h lun_heads_fwd): gate, quality[0..E), semantic, style,
+    prompt. Each entry: (LayerNorm or None, first Linear, Dropout, second Linear, dropout-trace tag)."""
+    g = teacher.gate
+    out = [(None, g[2], g[4], g[5], "gate_drop")]
+    for e, q in enumerate(teacher.quality_heads):
+        out.append((q[2], q[3], q[5], q[6], f"quality_drop.{e}"))
+    for seq, tag in ((teacher.semantic_head, "semantic_drop"), (teacher.style_net, "style_drop"),
+                     (teacher.prompt_net, "prompt_drop")):
+        out.append((seq[2], seq[3], seq[5], seq[6], tag))
+    return out
+
+
+def _head_params(teacher):
+    """Flat parameter list of the heads, 6 slots per head {ln.weight, ln.bias, l1.weight, l1.bias, l2.weight, l2.bias}
+    (the gate has no LayerNorm: 4 tensors)."""
+    ps = []
+    for ln, l1, _, l2, _ in _head_modules(teacher):
+        if ln is not None:
+            ps += [ln.weight, ln.bias]
+        ps += [l1.weight, l1.bias, l2.weight, l2.bias]
+    return ps
+
+
+class _HeadsFn(torch.autograd.Function):
+    """(pooled FE sums [B,128], pooled expert sums [E,B,C]) -> (quality_scores, expert_weights, style_embedding,
+    prompt_embedding, semantic_score): lunar_evaluator.py:417-456 in one launch (csrc/teacher_heads.cu); backward in
+    two. Gradients flow to the pooled expert sums and to every head parameter whose output reaches the loss; the
+    feature-extractor sums take none (detach rule (i))."""
+
+    @staticmethod
+    def _tables(teacher, B, seeds):
+        mods = _head_modules(teacher)
+        E = teacher.num_experts
+        ptrs = []
+        for ln, l1, _, l2, _ in mods:
+            for t in ((ln.weight, ln.bias) if ln is not None else (None, None)) + (l1.weight, l1.bias, l2.weight, l2.bias):
+                if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                    raise _capi.LunarisB200Error("Teacher head parameters must be contiguous fp32")
+                ptrs.append(0 if t is None else t.data_ptr())
+        params = (_capi.ctypes.c_void_p * len(ptrs))(*ptrs)
+        dims = (_capi.ctypes.c_int * 10)(B, E, mods[0][1].in_features, teacher.feature_dim, teacher.embedding_dim,
+                                          mods[0][1].out_features, mods[1][1].out_features,
+                                          mods[E + 1][1].out_features, mods[E + 2][1].out_features,
+                                          mods[E + 3][1].out_features)
+        seed_arr = (_capi.ctypes.c_ulonglong * (E + 4))(*seeds)
+        return params, dims, seed_arr
+
+    @staticmethod
+    def forward(ctx, teacher, inv_hw, grad_on, pooled_fe, pooled, *params):
+        lib = _capi.lib()
+        mods = _head_modules(teacher)
+        E, C, emb = teacher.num_experts, teacher.feature_dim, teacher.embedding_dim
+        B = pooled_fe.shape[0]
+        dev = pooled_fe.device
+        training = teacher.training
+        ctx.set_materialize_grads(False)       # unused outputs must stay None: their heads then keep grad None
+        p = float(mods[0][2].p) if training else 0.0
+        if training and any(float(m[2].p) != p for m in mods):
+            raise _capi.LunarisB200Error("the fused heads kernel takes one dropout probability for all heads")
+        seeds = [_cpu_seed(m[4], B, m[1].out_features) if p > 0 else 0 for m in mods]
+        tabs = _HeadsFn._tables(teacher, B, seeds)
+        sizes = (_capi.ctypes.c_int * 3)()
+        check(lib.lun_heads_buffer_sizes(tabs[1], sizes), "lun_heads_buffer_sizes")
+        pooled_fe = pooled_fe.detach().float().contiguous()
+        pooled = pooled.detach().float().contiguous()
+        f32 = dict(device=dev, dtype=torch.float32)
+        quality, weights = torch.empty(B, 4, **f32), torch.empty(B, E, **f32)
+        style, prompt, sem = torch.empty(B, emb, **f32), torch.empty(B, emb, **f32), torch.empty(B, 1, **f32)
+        save = torch.empty(B, sizes[0], **f32) if grad_on else None
+        check(lib.lun_heads_fwd(tabs[0], tabs[1], tabs[2], inv_hw, _SLOPE, p, 1 if training else 0,
+                                pooled_fe.data_ptr(), pooled.data_ptr(), quality.data_ptr(), weights.data_ptr(),
+                                style.data_ptr(), prompt.data_ptr(), sem.data_ptr(), _p(save), _stream()),
+              "lun_heads_fwd")
+        if grad_on:
+            ctx.teacher, ctx.inv_hw, ctx.p, ctx.seeds, ctx.sizes = teacher, inv_hw, p, seeds, tuple(sizes)
+            ctx.save_for_backward(pooled_fe, pooled, weights, save)
+        return quality, weights, style, prompt, sem
+
+    @staticmethod
+    def backward(ctx, g_quality, g_weights, g_style, g_prompt, g_sem):
+        lib = _capi.lib()
+        teacher = ctx.teacher
+        pooled_fe, pooled, weights, save = ctx.saved_tensors
+        E, C = teacher.num_experts, teacher.feature_dim
+        B = pooled_fe.shape[0]
+        dev = pooled_fe.device
+        tabs = _HeadsFn._tables(teacher, B, ctx.seeds)
+        f32 = dict(device=dev, dtype=torch.float32)
+        gs = [None if g is None else g.detach().float().contiguous() for g in (g_quality, g_weights, g_style, g_prompt, g_sem)]
+        # which heads' parameters take a gradient: those whose output reaches an incoming gradient
+        wants = [gs[0] is not None or gs[1] is not None or gs[2] is not None or gs[3] is not None]      # gate
+        wants += [gs[0] is not None] * E                                                               # quality heads
+        wants += [gs[4] is not None, gs[2] is not None, gs[3] is not None]                             # semantic, style, prompt
+        mods = _head_modules(teacher)
+        grads, ptrs = [], []
+        for (ln, l1, _, l2, _), want in zip(mods, wants):
+            row = []
+            for t in ((ln.weight, ln.bias) if ln is not None else (None, None)) + (l1.weight, l1.bias, l2.weight, l2.bias):
+                g = torch.empty_like(t) if (want and t is not None and t.requires_grad) else None
+                row.append(g)
+                ptrs.append(0 if g is None else g.data_ptr())
+            grads += row[2:] if ln is None else row
+        gtab = (_capi.ctypes.c_void_p * len(ptrs))(*ptrs)
+        dpre = torch.empty(B, ctx.sizes[1], **f32)
+        dout2 = torch.empty(B, ctx.sizes[2], **f32)
+        dxn = torch.empty(E + 3, B, C, **f32)
+        d_pooled = torch.empty(E, B, C, **f32)
+        check(lib.lun_heads_bwd(tabs[0], tabs[1], tabs[2], ctx.inv_hw, _SLOPE, ctx.p, pooled_fe.data_ptr(),
+                                pooled.data_ptr(), weights.data_ptr(), save.data_ptr(), _p(gs[0]), _p(gs[1]), _p(gs[2]),
+                                _p(gs[3]), _p(gs[4]), dpre.data_ptr(), dout2.data_ptr(), dxn.data_ptr(),
+                                d_pooled.data_ptr(), gtab, _stream()), "lun_heads_bwd")
+        return (None, None, None, None, d_pooled, *grads)
 
 
 _warned = set()
@@ -270,10 +360,11 @@ def _packed(param, kind):
 _stream = _capi.raw_stream
 
 
-def _cpu_seed(tag):
-    """Seed of one counter-RNG dropout launch, drawn from torch's CPU generator (rank r is seeded with seed + r)."""
+def _cpu_seed(tag, *shape):
+    """Seed of one counter-RNG dropout launch, drawn from torch's CPU generator (rank r is seeded with seed + r).
+    `shape` (head dropouts: [B, hidden]) goes to the dropout trace with the seed."""
     seed = int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
-    _host.trace("seed", tag, seed)
+    _host.trace("seed", tag, (seed, *shape) if shape else seed)
     return seed
 
 
@@ -366,7 +457,8 @@ def _fe_forward(fe, x, n_updates):
 def _folded_attention_weights(att):
     """Weight-only precompute for the K/V-free attention (refreshed when qkv changes; in reference mode it never
     does - qkv receives no gradient): Mq [8C, C] = Wk_h^T Wq_h / sqrt(hd) stacked over heads, cq [8C] = Wk_h^T bq_h /
-    sqrt(hd), and the value projection per head Wv [h][hd][C]. bf16 operands, fp32 products."""
+    sqrt(hd), and the value projection per head Wv [h][hd][C] (lun_head_linear_bf16: eight [hd, C] GEMMs in one launch
+    instead of a block-diagonal [C, 8C] one). bf16 operands, fp32 products."""
     w, bq = att.qkv.weight, att.qkv.bias
 
     def build():
@@ -377,11 +469,8 @@ def _folded_attention_weights(att):
         scale = float(torch.tensor(hd ** -0.5).to(torch.bfloat16))
         mq = torch.einsum("hdk,hdc->hkc", wf[1], wf[0]).mul_(scale).reshape(h * C, C)
         cq = torch.einsum("hdk,hd->hk", wf[1], bf[0]).mul_(scale).reshape(h * C)
-        wv = torch.zeros(C, h * C, device=w.device)
-        for i in range(h):
-            wv[i * hd:(i + 1) * hd, i * C:(i + 1) * C] = wf[2, i]
-        return (mq.to(torch.bfloat16).contiguous(), cq.contiguous(), wv.to(torch.bfloat16).contiguous(),
-                bf[2].reshape(C).contiguous())
+        wv = wf[2].to(torch.bfloat16).contiguous()                               # [head][d][c]: one GEMM per head
+        return (mq.to(torch.bfloat16).contiguous(), cq.contiguous(), wv, bf[2].reshape(C).contiguous())
     return _host.cached(att, "fold", (w, bq), build)
 
 
@@ -400,24 +489,20 @@ def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save, tag):
     p_attn = att.attn_drop.p if training else 0.0
     p_proj = att.proj_drop.p if training else 0.0
     att._touch_rel_pos(H, W, y1.device)
-    mq, cq, wv_bd, bv = _folded_attention_weights(att)
+    mq, cq, wv, bv = _folded_attention_weights(att)
+    # rows nq .. nq_pad-1 of xq / qt / xbar are padding that no kernel reads back; att_small's are zeroed below
     xq = torch.empty(B, nq_pad, C, device=y1.device, dtype=torch.bfloat16)
-    if nq_pad > nq:
-        xq[:, nq:].zero_()                       # only the padding rows need defined contents
     check(lib.lun_gather_query_rows_affine_bf16(y1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), _p(m1), xq.data_ptr(),
                                                 B, HW, C, nq_pad, _stream()), "lun_gather_query_rows_affine_bf16")
     qt = ops.linear_fprop(xq.view(B * nq_pad, C), mq, cq, out_f32=False)              # [B*nq_pad, heads*C]
-    xbar = torch.empty(B, nq_pad, heads * C, device=y1.device, dtype=torch.bfloat16)
-    if nq_pad > nq:
-        xbar[:, nq:].zero_()
-    xbar = xbar.view(B * nq_pad, heads * C)
+    xbar = torch.empty(B * nq_pad, heads * C, device=y1.device, dtype=torch.bfloat16)
     seed_attn = _cpu_seed(tag + ".attn_drop") if p_attn > 0 else 0
     check(lib.lun_attn_fold_rows_bf16(y1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), _p(m1), qt.data_ptr(),
                                       xbar.data_ptr(), B, HW, C, heads, nq_pad, seed_attn, float(p_attn), _stream()),
           "lun_attn_fold_rows_bf16")
-    att_small = ops.linear_fprop(xbar, wv_bd, bv, out_f32=False).view(B, nq_pad, C)
+    att_small = ops.head_linear(xbar, wv, bv).view(B, nq_pad, C)
     if nq_pad > nq:
-        att_small[:, nq:].zero_()
+        att_small[:, nq:].zero_()                # padding rows enter proj's weight gradient: they must be finite
     wp = _packed(att.proj.weight, "fwd")
     proj_small = ops.linear_fprop(att_small.view(B * nq_pad, C), wp.view(C, C), _packed(att.proj.bias, "f32"),
                                   out_f32=False)
@@ -513,51 +598,49 @@ def _block_tail_backward(B, HW, C, dout, gpool, out, bn_in, mean, rstd, gamma, l
 
 
 class _TeacherTrunk(torch.autograd.Function):
-    """images -> (sum-pooled FE features, sum-pooled expert outputs[, feature maps in eval]) with the reference's
-    executed gradient set as backward."""
+    """images -> (sum-pooled FE features [B,128], sum-pooled expert outputs [E,B,C][, feature maps in eval]) with the
+    reference's executed gradient set as backward."""
 
     @staticmethod
     def forward(ctx, teacher, x, grad_on, *params):
         B, _, H, W = x.shape
         training = teacher.training
         feats, pooled_fe = _fe_forward(teacher.feature_extractor, x, 1)
-        pooled, fmaps, saved = [], [], []
+        fmaps, saved = [], []
+        C = teacher.feature_dim
+        pooled = torch.zeros(len(teacher.experts), B, C, device=x.device)    # per-image channel sums of every expert
         for e, expert in enumerate(teacher.experts):
             h = feats
             per = []
-            C = expert[0].conv1[0].out_channels
             for b, blk in enumerate(expert):
                 last = b == len(expert) - 1
-                pool = torch.zeros(B, C, device=x.device) if last else None
                 # blocks whose checkpoint segment the reference re-runs in backward update BN stats twice
                 recomputed = grad_on and b > 0
-                h, sv = _block_forward(blk, h, B, H, W, training, 2 if recomputed else 1, save=grad_on, pool=pool,
-                                       tag=f"experts.{e}.{b}")
+                h, sv = _block_forward(blk, h, B, H, W, training, 2 if recomputed else 1, save=grad_on,
+                                       pool=pooled[e] if last else None, tag=f"experts.{e}.{b}")
                 per.append(sv)
-                if last:
-                    pooled.append(pool)
             saved.append(per)
             if not training:
                 fmaps.append(h)
         ctx.teacher, ctx.saved, ctx.grad_on = teacher, saved, grad_on
         ctx.dims = (B, H, W)
         ctx.feats = feats if grad_on else None
-        outs = (pooled_fe, *pooled, *fmaps)
+        outs = (pooled_fe, pooled, *fmaps)
         ctx.mark_non_differentiable(pooled_fe, *fmaps)
         return outs
 
     @staticmethod
-    def backward(ctx, g_fe, *gs):
+    def backward(ctx, g_fe, g_pooled, *g_maps):
         teacher = ctx.teacher
         B, H, W = ctx.dims
         HW = H * W
         grads = []
         for e, expert in enumerate(teacher.experts):
             C = expert[0].conv1[0].out_channels
-            gp = gs[e]
             per_block = {}
             dout = None
-            gpool = gp.contiguous().float() if gp is not None else torch.zeros(B, C, device=ctx.feats.device)
+            gpool = g_pooled[e].contiguous().float() if g_pooled is not None \
+                else torch.zeros(B, C, device=ctx.feats.device)
             for b in range(len(expert) - 1, 0, -1):
                 blk, sv = expert[b], ctx.saved[e][b]
                 gamma, beta = blk.conv2[2].weight.detach(), blk.conv2[2].bias.detach()
@@ -572,7 +655,9 @@ class _TeacherTrunk(torch.autograd.Function):
                 a = sv["att"]
                 # conv2's data gradient with proj_drop's backward folded into its epilogue: the proj bias gradient
                 # (column sums of mask * dh2 / (1-p)) comes out of the conv, only the nq surviving rows are re-read
-                dpo = torch.zeros(B, a["nq_pad"], C, device=dz.device, dtype=torch.bfloat16)
+                dpo = torch.empty(B, a["nq_pad"], C, device=dz.device, dtype=torch.bfloat16)
+                if a["nq_pad"] > a["nq"]:
+                    dpo[:, a["nq"]:].zero_()        # the gather kernel writes rows < nq; padding rows must be zero
                 if ops.drop_sum_ok(B, H, W, C):
                     colsum = torch.zeros(2 * C, device=dz.device)
                     dh2 = ops.conv2d_dgrad(dz4, _packed(blk.conv2[0].weight, "dgrad"), 3, 1, 1, (H, W),

@@ -204,7 +204,7 @@ class LunarisCoreVAE(nn.Module):
             raise _capi.LunarisB200Error("lunaris_orion_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         B = x.shape[0]
         # first RNG draw of the step, same call and shape as the reference's randn_like (lunar_generate.py:260)
-        eps = torch.randn(B, self.latent_dim, device=x.device, dtype=torch.float32)
+        eps = _host.draw_eps(B, self.latent_dim, x.device)
         params = list(self.parameters())
         return _VAEFn.apply(self, x.detach(), eps, *params)
 

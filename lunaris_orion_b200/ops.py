@@ -246,6 +246,18 @@ def linear_fprop(x, w_bf16, bias=None, out_f32=True):
     return out
 
 
+def head_linear(x, w_heads, bias=None):
+    """`heads` independent Linears in one launch: x [rows, heads*cin] bf16, w_heads [heads, cout, cin] bf16,
+    bias [heads*cout] fp32 -> [rows, heads*cout] bf16 (the per-head value projection of the as-executed attention)."""
+    rows = x.shape[0]
+    heads, cout, cin = w_heads.shape
+    assert x.shape[1] == heads * cin and x.is_contiguous() and w_heads.is_contiguous()
+    out = torch.empty(rows, heads * cout, device=x.device, dtype=torch.bfloat16)
+    check(_capi.lib().lun_head_linear_bf16(x.data_ptr(), rows, heads, cin, w_heads.data_ptr(), cout, _ptr(bias),
+                                           out.data_ptr(), _stream()), "lun_head_linear_bf16")
+    return out
+
+
 def linear_dgrad(dy, w_t_bf16):
     """dx = dy @ W with W^T packed as [K,N] bf16; dy [B,N] bf16 -> [B,K] bf16."""
     B, N = dy.shape

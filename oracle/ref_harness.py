@@ -1,7 +1,7 @@
 """Drive the UNMODIFIED reference trainer (train_hybrid.TrainingManager) without its CLI loop - SURVEY.md App. C.1.
 
-The bare CLI crashes on torch >= 2.11 with num_workers 0 (DataLoader timeout assertion), so the harness
-shims the one DataLoader kwarg, replaces `TrainingManager.train` by a capture, lets the reference's own `main()` parse
+The bare CLI crashes on torch >= 2.11 with num_workers 0 (DataLoader timeout assertion; on CUDA also
+prefetch_factor / persistent_workers without workers), so the harness shims those DataLoader kwargs, replaces `TrainingManager.train` by a capture, lets the reference's own `main()` parse
 flags / seed / construct everything, and hands back the TrainingManager whose `_process_batch` the caller then drives.
 Works from sources (/root/reference) and from oracle/_ref bytecode. TEST / BENCH INFRASTRUCTURE ONLY.
 """
@@ -44,8 +44,15 @@ def import_reference_trainer(dropin=False):
     import train_hybrid as th
     if not getattr(th, "_lun_dl_shim", False):
         _DL = th.DataLoader
-        th.DataLoader = lambda ds, **kw: _DL(ds, **{**kw, "timeout": 0 if kw.get("num_workers", 0) == 0
-                                                      else kw.get("timeout", 0)})
+
+        def loader(ds, **kw):
+            # num_workers 0: torch >= 2.11 asserts timeout == 0 and rejects the prefetch_factor /
+            # persistent_workers / multiprocessing_context the reference passes on CUDA (train_hybrid.py:561-570)
+            if kw.get("num_workers", 0) == 0:
+                kw = {**kw, "timeout": 0, "prefetch_factor": None, "persistent_workers": False,
+                      "multiprocessing_context": None}
+            return _DL(ds, **kw)
+        th.DataLoader = loader
         th._lun_dl_shim = True
     return th
 

@@ -80,6 +80,10 @@ def oracle_masks(events, B, H, W, feat, p):
             masks[tag] = nhwc_mask_as_nchw(val, B, H, W, feat, p)
         elif kind == "seed" and tag.endswith(".attn_drop"):
             masks[tag] = attention_mask(val, B, 8, N, p)
+        elif kind == "seed" and isinstance(val, tuple):        # head dropouts: (seed, B, hidden), index = b * hidden + j
+            seed, nb, hidden = val
+            k = keep_range(seed, nb * hidden, p).reshape(nb, hidden)
+            masks[tag] = torch.from_numpy(k.astype(np.float32)) / (1.0 - p)
         elif kind == "mask2d":
             masks[tag] = (val.detach().cpu().float() / (1.0 - p)).view(B, -1, 1, 1)
         elif kind == "mask":

@@ -106,32 +106,45 @@ def train_report(dev, B=2):
     return rep
 
 
-def _trunk_oracle(x, sd, G, autocast_dev=None):
+def _trunk_oracle(x, sd, G, autocast_dev=None, masks=None):
     """Oracle trunk loss sum_e <pooled_e, G_e> / HW and its parameter gradients (fp32 CPU, or bf16 autocast on GPU
     to calibrate how far a bf16 execution of the reference op sequence drifts from fp32)."""
     import contextlib
     ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast_dev is not None else contextlib.nullcontext()
     with ctx:
-        fe, outs = R.teacher_trunk(x, sd, training=True)
+        fe, outs = R.teacher_trunk(x, sd, training=True, masks=masks)
         pooled = [o.float().sum((2, 3)) for o in outs]
         loss = sum((p * g).sum() for p, g in zip(pooled, G)) / (x.shape[2] * x.shape[3])
     loss.backward()
     return fe.detach().float().sum((2, 3)), [p.detach() for p in pooled]
 
 
-def trunk_report(dev, B=2, feat=64, calibrate=True):
-    from lunaris_orion_b200 import lunar_evaluator as le
-    t = make_teacher(dev, feat=feat).train()
+def trunk_report(dev, B=2, feat=64, calibrate=True, dropout=0.0):
+    """Trunk forward + backward (pooled expert outputs contracted with fixed random cotangents G) vs the oracle.
+    dropout > 0: every dropout of the trunk is ON; the masks the CUDA path drew are rebuilt from its dropout trace
+    (tests/dropout_rng.py) and injected into the oracle, so the comparison stays elementwise."""
+    from lunaris_orion_b200 import _host, lunar_evaluator as le
+    t = make_teacher(dev, feat=feat, dropout=dropout).train()
     x = images(B, seed=8)
     g = torch.Generator().manual_seed(9)
     G = [torch.randn(B, feat, generator=g) for _ in range(4)]
     HW = 128 * 128
     # mine
     params = le._trunk_grad_params(t)
-    res = le._TeacherTrunk.apply(t, x.to(dev), True, *params)
-    loss = sum((p * gg.to(dev)).sum() for p, gg in zip(res[1:5], G)) / HW
+    trace = []
+    _host.set_dropout_trace(trace if dropout > 0 else None)
+    try:
+        res = le._TeacherTrunk.apply(t, x.to(dev), True, *params)
+    finally:
+        _host.set_dropout_trace(None)
+    masks = None
+    if dropout > 0:
+        import dropout_rng
+        assert len(trace) == 1 + 12 * 4, [e[1] for e in trace]
+        masks = dropout_rng.oracle_masks(trace, B, 128, 128, feat, dropout)
+    loss = sum((res[1][e] * gg.to(dev)).sum() for e, gg in enumerate(G)) / HW
     loss.backward()
-    mine_pool = [r.detach().cpu() for r in res[1:5]]
+    mine_pool = [res[1][e].detach().cpu() for e in range(4)]
     mine_fe = res[0].detach().cpu()
     mine_grads = {n: p.grad.detach().cpu().float() for n, p in t.named_parameters() if p.grad is not None}
     # oracle fp32 (CPU)
@@ -139,9 +152,9 @@ def trunk_report(dev, B=2, feat=64, calibrate=True):
     for k in sd:
         if "running_" in k or k.endswith("num_batches_tracked"):
             pass
-    t2 = make_teacher(dev, feat=feat)          # fresh buffers for the oracle (same seed => same params)
+    t2 = make_teacher(dev, feat=feat, dropout=dropout)   # fresh buffers for the oracle (same seed => same params)
     sd = oracle_sd(t2)
-    ref_fe, ref_pool = _trunk_oracle(x, sd, G)
+    ref_fe, ref_pool = _trunk_oracle(x, sd, G, masks=masks)
     ref_grads = {n: sd[n].grad for n, _ in t2.named_parameters() if sd[n].grad is not None}
     rep = {"fe_pool": rel_err(mine_fe, ref_fe),
            "pool": max(rel_err(a, b) for a, b in zip(mine_pool, ref_pool)),
@@ -160,10 +173,11 @@ def trunk_report(dev, B=2, feat=64, calibrate=True):
     rep["grad_rel_max"] = max(ge.values())
     rep["grad_worst"] = sorted(ge.items(), key=lambda kv: -kv[1])[:5]
     if calibrate:
-        sdc = {k: v.detach().to(dev) for k, v in oracle_sd(make_teacher(dev, feat=feat)).items()}
+        sdc = {k: v.detach().to(dev) for k, v in oracle_sd(make_teacher(dev, feat=feat, dropout=dropout)).items()}
         for n, _ in t2.named_parameters():
             sdc[n].requires_grad_(True)
-        cal_fe, cal_pool = _trunk_oracle(x.to(dev), sdc, [gg.to(dev) for gg in G], autocast_dev=dev)
+        cal_fe, cal_pool = _trunk_oracle(x.to(dev), sdc, [gg.to(dev) for gg in G], autocast_dev=dev,
+                                         masks=None if masks is None else {k: v.to(dev) for k, v in masks.items()})
         cal_grads = {n: sdc[n].grad.detach().cpu().float() for n in ref_grads if sdc[n].grad is not None}
         ce = grad_errs(cal_grads)
         rep["cal_pool"] = max(rel_err(a, b) for a, b in zip(cal_pool, ref_pool))
@@ -209,3 +223,23 @@ def sample_agreement(named_tensors, ref_fps, skip=("shortcut.0.bias",)):
     return {"cosine": float((a @ b) / (a.norm() * b.norm() + 1e-30)), "sign_agree": sign_ok / max(sign_n, 1),
             "n_significant": sign_n, "value_within_10pct": val_ok / max(val_n, 1), "n_samples": val_n,
             "worst_tensor": max(per.items(), key=lambda kv: kv[1])}
+
+
+
+class reference_eps:
+    """Context manager: LunarisCoreVAE.forward takes its reparameterisation noise from the CPU generator stream the
+    reference trainer used for the golden fixtures (`torch.manual_seed(seed)` once, then one `randn_like(std)` per
+    step on CPU; with dropout probabilities 0 nothing else draws from it) instead of the CUDA generator."""
+
+    def __init__(self, seed):
+        self.gen = torch.Generator().manual_seed(seed)
+
+    def __enter__(self):
+        from lunaris_orion_b200 import _host
+        _host.set_eps_source(lambda b, l, dev: torch.randn(b, l, generator=self.gen))
+        return self
+
+    def __exit__(self, *exc):
+        from lunaris_orion_b200 import _host
+        _host.set_eps_source(None)
+        return False

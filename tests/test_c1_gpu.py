@@ -35,8 +35,9 @@ def test_two_trainer_steps_at_c1_match_the_reference_trainer(cuda_dev, tmp_path)
         if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout2d)):
             m.p = 0.0
     x = tc.images(cfg["B"], cfg["img_seed"]).to(cuda_dev)
-    torch.manual_seed(cfg["eps_seed"])
-    m0 = tm._process_batch(x, 0)
+    eps = tc.reference_eps(cfg["eps_seed"])        # the reference's CPU-generator noise, step after step
+    with eps:
+        m0 = tm._process_batch(x, 0)
     ref0 = gold["step0"]
 
     report = {"step0": {k: (m0[k], ref0["metrics"][k]) for k in ref0["metrics"]}}
@@ -88,7 +89,8 @@ def test_two_trainer_steps_at_c1_match_the_reference_trainer(cuda_dev, tmp_path)
     report["grad_sample_agreement"] = agree
     report["param_samples_stepped_in_opposite_direction"] = flips
 
-    m1 = tm._process_batch(x, 1)
+    with eps:
+        m1 = tm._process_batch(x, 1)
     ref1 = gold["step1"]
     report["step1"] = {k: (m1[k], ref1["metrics"][k]) for k in ref1["metrics"]}
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
@@ -110,7 +112,8 @@ def test_two_trainer_steps_at_c1_match_the_reference_trainer(cuda_dev, tmp_path)
     # third consecutive step (">= 3 consecutive steps"): two optimizer updates deep, the bf16 path and the
     # fp32 reference have drifted apart a little more; BatchNorm counters and the schedule stay exact
     if "step2" in gold:
-        m2 = tm._process_batch(x, 2)
+        with eps:
+            m2 = tm._process_batch(x, 2)
         ref2 = gold["step2"]
         report["step2"] = {k: (m2[k], ref2["metrics"][k]) for k in ref2["metrics"]}
         if os.path.isdir(out_dir):

@@ -44,7 +44,7 @@ def test_accumulation_window_at_c2_matches_the_reference_trainer(cuda_dev, tmp_p
     probe = tm.vae.decoder.final_conv.weight
     w0 = probe.detach().clone()
     lr0 = tm.vae_optimizer.param_groups[0]["lr"]
-    torch.manual_seed(cfg["eps_seed"])
+    eps = tc.reference_eps(cfg["eps_seed"])        # the reference's CPU-generator noise, call after call
     report = {"calls": []}
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 
@@ -54,7 +54,8 @@ def test_accumulation_window_at_c2_matches_the_reference_trainer(cuda_dev, tmp_p
 
     for i, ref in enumerate(gold["calls"]):
         x = tc.images(cfg["B"], cfg["img_seed"] + i).to(cuda_dev)
-        m = tm._process_batch(x, i)
+        with eps:
+            m = tm._process_batch(x, i)
         rm = ref["metrics"]
         report["calls"].append({k: (m[k], rm[k]) for k in rm})
         dump()

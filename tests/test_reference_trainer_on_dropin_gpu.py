@@ -25,7 +25,7 @@ CFG = gold["cfg"]
 def test_unmodified_reference_trainer_steps_on_the_dropin_modules(cuda_dev, tmp_path):
     cmd = [sys.executable, os.path.join(ROOT, "tools", "run_reference_on_dropin.py"), "--steps", "2", "--dropout", "0",
            "--batch", str(CFG["B"]), "--latent", str(CFG["latent"]), "--emb", str(CFG["emb"]), "--feat", str(CFG["feat"]),
-           "--img-seed", str(CFG["img_seed"]), "--eps-seed", str(gold["trainer_step"]["eps_seed"])]
+           "--img-seed", str(CFG["img_seed"]), "--eps-seed", str(gold["trainer_step"]["eps_seed"]), "--cpu-eps"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     rep = json.loads(out.stdout.strip().splitlines()[-1])
@@ -55,8 +55,8 @@ def test_unmodified_reference_trainer_steps_on_the_dropin_modules(cuda_dev, tmp_
         if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout2d)):
             m.p = 0.0
     x = tc.images(CFG["B"], CFG["img_seed"]).to(cuda_dev)
-    torch.manual_seed(gold["trainer_step"]["eps_seed"])
-    mine = [tm._process_batch(x, i) for i in range(2)]
+    with tc.reference_eps(gold["trainer_step"]["eps_seed"]):
+        mine = [tm._process_batch(x, i) for i in range(2)]
     for s in range(2):
         for k in ("recon_loss", "kl_loss", "vae_loss", "quality_scores", "teacher_loss", "baseline"):
             a, b = rep["steps"][s][k], mine[s][k]

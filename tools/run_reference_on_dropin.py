@@ -27,6 +27,8 @@ def main():
     p.add_argument("--dropout", type=float, default=None, help="override every dropout probability (0 = deterministic)")
     p.add_argument("--img-seed", type=int, default=5)
     p.add_argument("--eps-seed", type=int, default=123)
+    p.add_argument("--cpu-eps", action="store_true",
+                   help="take the VAE noise from the CPU generator stream (what the golden fixtures were made with)")
     a = p.parse_args()
     import torch
     from oracle import ref_harness
@@ -51,6 +53,10 @@ def main():
     x = (torch.randint(0, 256, (a.batch, 3, 128, 128), generator=g, dtype=torch.uint8).float() / 127.5 - 1.0).to(tm.device)
     l0 = _capi.lib().lun_launch_count()
     torch.manual_seed(a.eps_seed)
+    if a.cpu_eps:
+        from lunaris_orion_b200 import _host
+        gen = torch.Generator().manual_seed(a.eps_seed)
+        _host.set_eps_source(lambda b, l, dev: torch.randn(b, l, generator=gen))
     steps = [tm._process_batch(x, i) for i in range(a.steps)]
     launches = _capi.lib().lun_launch_count() - l0
     tm._save_checkpoint()
