@@ -126,7 +126,10 @@ SIGNATURES = {
 
 
 def _declare(l):
+    older_build = bool(os.environ.get("LUNARIS_B200_LIB"))      # an A/B build may predate the newest entry points
     for name, argtypes in SIGNATURES.items():
+        if older_build and not hasattr(l, name):
+            continue
         fn = getattr(l, name)
         fn.argtypes = argtypes
         fn.restype = ctypes.c_longlong if name == "lun_launch_count" else c_int

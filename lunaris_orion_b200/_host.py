@@ -86,3 +86,49 @@ def draw_eps(batch, latent_dim, device):
     if _eps_source is not None:
         return _eps_source(batch, latent_dim, device).to(device=device, dtype=torch.float32).contiguous()
     return torch.randn(batch, latent_dim, device=device, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------ zero pool
+# A forward or backward pass needs ~200 small zero-initialised fp32 buffers (BatchNorm / GroupNorm sums, pooling
+# accumulators, reduction targets of the fused epilogues). Inside `with zero_pool(device):` they are slices of ONE block
+# that a single memset clears, instead of one fill launch each; the block is sized from the largest pass seen so far.
+_pool = None
+_pool_need = {}
+
+
+class zero_pool:
+    def __init__(self, device):
+        self.key = str(device)
+        self.device = device
+
+    def __enter__(self):
+        global _pool
+        self.prev = _pool
+        self.buf = torch.zeros(_pool_need.get(self.key, 1 << 16), device=self.device, dtype=torch.float32)
+        self.off = self.total = 0
+        _pool = self
+        return self
+
+    def __exit__(self, *exc):
+        global _pool
+        _pool = self.prev
+        if self.total > _pool_need.get(self.key, 0):
+            _pool_need[self.key] = self.total + (self.total >> 3)
+        return False
+
+
+def zeros(*shape, device):
+    """fp32 zeros of `shape`: a 256-byte aligned slice of the active pool, or a plain torch.zeros outside one."""
+    p = _pool
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if p is None or str(device) != p.key or n > (1 << 20):
+        return torch.zeros(*shape, device=device, dtype=torch.float32)
+    n_al = (n + 63) & ~63
+    p.total += n_al
+    if p.off + n_al > p.buf.numel():
+        return torch.zeros(*shape, device=device, dtype=torch.float32)
+    v = p.buf[p.off:p.off + n].view(*shape)
+    p.off += n_al
+    return v

@@ -418,7 +418,7 @@ def _fe_forward(fe, x, n_updates):
 
     c1, bn1 = fe.conv1[0], fe.conv1[2]
     y0 = torch.empty(B, HW, 32, device=dev, dtype=torch.bfloat16)
-    st = torch.zeros(64, device=dev)
+    st = _host.zeros(64, device=dev)
     check(lib.lun_fe_conv1(x.data_ptr(), _packed(c1.weight, "f32").data_ptr(), _packed(c1.bias, "f32").data_ptr(),
                            y0.data_ptr(), st.data_ptr(), B, H, W, _SLOPE, _stream()), "lun_fe_conv1")
     sc0, sh0 = _bn_train(bn1, st, B * HW, n_updates)[:2] if training else _bn_eval(bn1)
@@ -431,7 +431,7 @@ def _fe_forward(fe, x, n_updates):
     check(lib.lun_fe_branches(y0.data_ptr(), sc0.data_ptr(), sh0.data_ptr(), arrs[0], arrs[1], arrs[2], arrs[3],
                               cat.data_ptr(), B, H, W, _SLOPE, _stream()), "lun_fe_branches")
     if training:
-        st = torch.zeros(2 * 192, device=dev)
+        st = _host.zeros(2 * 192, device=dev)
         check(lib.lun_channel_stats_bf16(cat.data_ptr(), B * HW, 192, st.data_ptr(), _stream()),
               "lun_channel_stats_bf16")
         sums, sqs = st[:192], st[192:]
@@ -445,11 +445,11 @@ def _fe_forward(fe, x, n_updates):
 
     cf, bnf = fe.fusion[0], fe.fusion[2]
     C = cf.out_channels
-    st = torch.zeros(2 * C, device=dev) if training else None
+    st = _host.zeros(2 * C, device=dev) if training else None
     f_pre = ops.conv2d_fprop(cat_n.view(B, H, W, 192), _packed(cf.weight, "fwd"), 1, 1, 0,
                              bias=_packed(cf.bias, "f32"), act_leaky=True, stats=st, slope=_SLOPE)
     scf, shf = _bn_train(bnf, st, B * HW, n_updates)[:2] if training else _bn_eval(bnf)
-    pooled = torch.zeros(B, C, device=dev)
+    pooled = _host.zeros(B, C, device=dev)
     feats = _affine(f_pre.view(B, HW, C), B, HW, C, scf, shf, pool=pooled)
     return feats, pooled
 
@@ -469,7 +469,13 @@ def _folded_attention_weights(att):
         scale = float(torch.tensor(hd ** -0.5).to(torch.bfloat16))
         mq = torch.einsum("hdk,hdc->hkc", wf[1], wf[0]).mul_(scale).reshape(h * C, C)
         cq = torch.einsum("hdk,hd->hk", wf[1], bf[0]).mul_(scale).reshape(h * C)
-        wv = wf[2].to(torch.bfloat16).contiguous()                               # [head][d][c]: one GEMM per head
+        if hd % 32 == 0:
+            wv = wf[2].to(torch.bfloat16).contiguous()                           # [head][d][c]: one GEMM per head
+        else:           # head_dim below the kernel's 32-channel output block (feature_dim < 256): block-diagonal [C, 8C]
+            wv = torch.zeros(C, h * C, device=w.device)
+            for i in range(h):
+                wv[i * hd:(i + 1) * hd, i * C:(i + 1) * C] = wf[2, i]
+            wv = wv.to(torch.bfloat16).contiguous()
         return (mq.to(torch.bfloat16).contiguous(), cq.contiguous(), wv, bf[2].reshape(C).contiguous())
     return _host.cached(att, "fold", (w, bq), build)
 
@@ -500,7 +506,8 @@ def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save, tag):
     check(lib.lun_attn_fold_rows_bf16(y1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), _p(m1), qt.data_ptr(),
                                       xbar.data_ptr(), B, HW, C, heads, nq_pad, seed_attn, float(p_attn), _stream()),
           "lun_attn_fold_rows_bf16")
-    att_small = ops.head_linear(xbar, wv, bv).view(B, nq_pad, C)
+    att_small = (ops.head_linear(xbar, wv, bv) if wv.dim() == 3
+                 else ops.linear_fprop(xbar, wv, bv, out_f32=False)).view(B, nq_pad, C)
     if nq_pad > nq:
         att_small[:, nq:].zero_()                # padding rows enter proj's weight gradient: they must be finite
     wp = _packed(att.proj.weight, "fwd")
@@ -514,8 +521,34 @@ def _attention_forward(att, y1, sc1, sh1, m1, B, H, W, training, save, tag):
     return h2, saved
 
 
-def _block_forward(blk, x, B, H, W, training, n_updates, save, pool, tag):
-    """ExpertBlock.forward (lunar_evaluator.py:260-275) on NHWC bf16 x [B,HW,Cin]. Returns (out [B,HW,C], saved)."""
+def _input_moments(x, B, HW, Cin):
+    """First and second moments of a block input over all pixels: (sum x [Cin], sum x x^T [Cin,Cin]), fp32. The Gram
+    matrix is one launch of the tcgen05 weight-gradient kernel (dY = X)."""
+    st = _host.zeros(2 * Cin, device=x.device)
+    check(_capi.lib().lun_channel_stats_bf16(x.data_ptr(), B * HW, Cin, st.data_ptr(), _stream()),
+          "lun_channel_stats_bf16")
+    x4 = x.view(B, 1, HW, Cin)
+    gram = ops.conv2d_wgrad(x4, x4, 1, 1, 0).reshape(Cin, Cin)
+    return st[:Cin], gram
+
+
+def _shortcut_stats(conv, xmom, n):
+    """[sum y | sum y^2] per output channel of the 1x1 shortcut conv y = W x + b (ExpertBlock.shortcut[0],
+    lunar_evaluator.py:254-257) WITHOUT reading y: the conv is linear and feeds its BatchNorm directly, so
+    sum y = W sum(x) + n b and sum y^2 = diag(W G W^T) + 2 b (W sum x) + n b^2 with G = sum x x^T. The four experts share
+    one G, and the conv itself runs without the statistics epilogue (which cost it 2x: 0.43 -> 0.9 ms at C3)."""
+    sx, gram = xmom
+    w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).to(torch.bfloat16).float()
+    b = conv.bias.detach().float()
+    wsx = w @ sx
+    s1 = wsx + n * b
+    s2 = ((w @ gram) * w).sum(1) + 2.0 * b * wsx + n * b * b
+    return torch.cat([s1, s2]).contiguous()
+
+
+def _block_forward(blk, x, B, H, W, training, n_updates, save, pool, tag, xmom=None):
+    """ExpertBlock.forward (lunar_evaluator.py:260-275) on NHWC bf16 x [B,HW,Cin]. Returns (out [B,HW,C], saved).
+    xmom: _input_moments(x) when the caller already has them (the experts' first blocks share one input)."""
     HW = H * W
     dev = x.device
     c1, bn1, d1 = blk.conv1[0], blk.conv1[2], blk.conv1[3]
@@ -523,7 +556,7 @@ def _block_forward(blk, x, B, H, W, training, n_updates, save, pool, tag):
     C, Cin = c1.out_channels, c1.in_channels
     p2d = d1.p if training else 0.0
 
-    st = torch.zeros(2 * C, device=dev) if training else None
+    st = _host.zeros(2 * C, device=dev) if training else None
     y1 = ops.conv2d_fprop(x.view(B, H, W, Cin), _packed(c1.weight, "fwd"), 3, 1, 1, bias=_packed(c1.bias, "f32"),
                           act_leaky=True, stats=st, slope=_SLOPE)
     sc1, sh1 = _bn_train(bn1, st, B * HW, n_updates)[:2] if training else _bn_eval(bn1)
@@ -531,7 +564,7 @@ def _block_forward(blk, x, B, H, W, training, n_updates, save, pool, tag):
     h2, att_saved = _attention_forward(blk.attention, y1.view(B, HW, C), sc1, sh1, m1, B, H, W, training, save, tag)
     del y1
 
-    st = torch.zeros(2 * C, device=dev) if training else None
+    st = _host.zeros(2 * C, device=dev) if training else None
     y2 = ops.conv2d_fprop(h2.view(B, H, W, C), _packed(c2.weight, "fwd"), 3, 1, 1, bias=_packed(c2.bias, "f32"),
                           act_leaky=True, stats=st, slope=_SLOPE).view(B, HW, C)
     if training:
@@ -543,10 +576,10 @@ def _block_forward(blk, x, B, H, W, training, n_updates, save, pool, tag):
     has_sc = not isinstance(blk.shortcut, nn.Identity)
     if has_sc:
         cs, bns = blk.shortcut[0], blk.shortcut[1]
-        st = torch.zeros(2 * C, device=dev) if training else None
         identity = ops.conv2d_fprop(x.view(B, H, W, Cin), _packed(cs.weight, "fwd"), 1, 1, 0,
-                                    bias=_packed(cs.bias, "f32"), stats=st).view(B, HW, C)
+                                    bias=_packed(cs.bias, "f32")).view(B, HW, C)
         if training:
+            st = _shortcut_stats(cs, xmom if xmom is not None else _input_moments(x, B, HW, Cin), float(B * HW))
             isc, ish, imean, irstd = _bn_train(bns, st, B * HW, n_updates)
         else:
             (isc, ish), imean, irstd = _bn_eval(bns), None, None
@@ -582,13 +615,13 @@ def _block_tail_backward(B, HW, C, dout, gpool, out, bn_in, mean, rstd, gamma, l
     Returns (dpre, dz, dbias_conv, t1, t2)."""
     lib = _capi.lib()
     dev = bn_in.device
-    t = torch.zeros(2, C, device=dev)
+    t = _host.zeros(2, C, device=dev)
     dpre = torch.empty(B, HW, C, device=dev, dtype=torch.bfloat16) if want_dpre else None
     check(lib.lun_block_bwd_reduce_bf16(_p(dout), _p(gpool), _p(out), bn_in.data_ptr(), mean.data_ptr(),
                                         rstd.data_ptr(), _p(m2), _p(dpre), t[0].data_ptr(), t[1].data_ptr(), B, HW, C,
                                         slope_out, _stream()), "lun_block_bwd_reduce_bf16")
     dz = torch.empty(B, HW, C, device=dev, dtype=torch.bfloat16)
-    dbias = torch.zeros(C, device=dev)
+    dbias = _host.zeros(C, device=dev)
     check(lib.lun_block_bwd_apply_bf16(_p(dpre), None if dpre is not None else _p(gpool),
                                        None if dpre is not None else _p(out), bn_in.data_ptr(), mean.data_ptr(),
                                        rstd.data_ptr(), gamma.data_ptr(), _p(ls), _p(m2), t[0].data_ptr(),
@@ -603,12 +636,18 @@ class _TeacherTrunk(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, teacher, x, grad_on, *params):
+        with _host.zero_pool(x.device):
+            return _TeacherTrunk._forward(ctx, teacher, x, grad_on)
+
+    @staticmethod
+    def _forward(ctx, teacher, x, grad_on):
         B, _, H, W = x.shape
         training = teacher.training
         feats, pooled_fe = _fe_forward(teacher.feature_extractor, x, 1)
         fmaps, saved = [], []
         C = teacher.feature_dim
-        pooled = torch.zeros(len(teacher.experts), B, C, device=x.device)    # per-image channel sums of every expert
+        pooled = _host.zeros(len(teacher.experts), B, C, device=x.device)    # per-image channel sums of every expert
+        xmom = _input_moments(feats, B, H * W, feats.shape[-1]) if training else None
         for e, expert in enumerate(teacher.experts):
             h = feats
             per = []
@@ -617,7 +656,8 @@ class _TeacherTrunk(torch.autograd.Function):
                 # blocks whose checkpoint segment the reference re-runs in backward update BN stats twice
                 recomputed = grad_on and b > 0
                 h, sv = _block_forward(blk, h, B, H, W, training, 2 if recomputed else 1, save=grad_on,
-                                       pool=pooled[e] if last else None, tag=f"experts.{e}.{b}")
+                                       pool=pooled[e] if last else None, tag=f"experts.{e}.{b}",
+                                       xmom=xmom if b == 0 else None)
                 per.append(sv)
             saved.append(per)
             if not training:
@@ -631,6 +671,11 @@ class _TeacherTrunk(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_fe, g_pooled, *g_maps):
+        with _host.zero_pool(ctx.feats.device):
+            return _TeacherTrunk._backward(ctx, g_pooled)
+
+    @staticmethod
+    def _backward(ctx, g_pooled):
         teacher = ctx.teacher
         B, H, W = ctx.dims
         HW = H * W
@@ -659,13 +704,13 @@ class _TeacherTrunk(torch.autograd.Function):
                 if a["nq_pad"] > a["nq"]:
                     dpo[:, a["nq"]:].zero_()        # the gather kernel writes rows < nq; padding rows must be zero
                 if ops.drop_sum_ok(B, H, W, C):
-                    colsum = torch.zeros(2 * C, device=dz.device)
+                    colsum = _host.zeros(2 * C, device=dz.device)
                     dh2 = ops.conv2d_dgrad(dz4, _packed(blk.conv2[0].weight, "dgrad"), 3, 1, 1, (H, W),
                                            drop_sum=(a["seed"], a["p_proj"], colsum))
                     dbp = colsum[:C]
                 else:                                # small feature maps: a separate pass sums the masked gradient
                     dh2 = ops.conv2d_dgrad(dz4, _packed(blk.conv2[0].weight, "dgrad"), 3, 1, 1, (H, W))
-                    dbp = torch.zeros(C, device=dz.device)
+                    dbp = _host.zeros(C, device=dz.device)
                 del dz, dz4
                 check(_capi.lib().lun_proj_bwd_gather_bf16(dh2.data_ptr(), dpo.data_ptr(),
                                                            None if ops.drop_sum_ok(B, H, W, C) else dbp.data_ptr(), B,

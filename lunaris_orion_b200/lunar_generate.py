@@ -260,14 +260,14 @@ def _conv_gn(B, hw, C, dev, conv_fn):
     image per tile), by a separate pass over t otherwise."""
     HW = hw * hw
     if ops.img_stats_ok(hw, hw):
-        st = torch.zeros(B, 2, C, device=dev, dtype=torch.float32)
+        st = _host.zeros(B, 2, C, device=dev)
         return conv_fn(st).view(B, HW, C), st
     t = conv_fn(None).view(B, HW, C)
     return t, _gn_stats(t, B, HW, C)
 
 
 def _gn_stats(t, B, HW, C):
-    st = torch.zeros(B, 2, C, device=t.device, dtype=torch.float32)
+    st = _host.zeros(B, 2, C, device=t.device)
     check(_capi.lib().lun_image_channel_stats_bf16(t.data_ptr(), st.data_ptr(), B, HW, C, _stream()),
           "lun_image_channel_stats_bf16")
     return st
@@ -283,7 +283,7 @@ def _gn_mish(t, st, gn, B, HW, C, res=None, add=None):
 
 def _gn_mish_bwd(dy, dy2, t, st, gn, B, HW, C, res=None, want_dres=False):
     """Returns (dt, dres, dgamma, dbeta)."""
-    red = torch.zeros(B, 2, C, device=t.device, dtype=torch.float32)
+    red = _host.zeros(B, 2, C, device=t.device)
     dt = torch.empty_like(t)
     dres = torch.empty_like(t) if want_dres else None
     check(_capi.lib().lun_gn_mish_bwd_bf16(dy.data_ptr(), _p(dy2), t.data_ptr(), st.data_ptr(),
@@ -296,7 +296,7 @@ def _gn_mish_bwd(dy, dy2, t, st, gn, B, HW, C, res=None, want_dres=False):
 
 def _colsum(t, P, C):
     """Per-channel sum of a bf16 [P,C] tensor (conv bias gradients)."""
-    st = torch.zeros(2 * C, device=t.device, dtype=torch.float32)
+    st = _host.zeros(2 * C, device=t.device)
     check(_capi.lib().lun_channel_stats_bf16(t.data_ptr(), P, C, st.data_ptr(), _stream()), "lun_channel_stats_bf16")
     return st[:C]
 
@@ -381,7 +381,7 @@ def _decoder_forward(dec, z, skips, save):
         convT, gn = up[0], up[1]
         cin, C = chans[i], chans[i + 1]
         if ops.img_stats_ok(hw, hw):               # each output phase grid is hw x hw per image
-            st = torch.zeros(B, 2, C, device=z.device, dtype=torch.float32)
+            st = _host.zeros(B, 2, C, device=z.device)
             t = ops.convT4x4s2_fprop(h.view(B, hw, hw, cin), _wT(convT), bias=_f32(convT.bias), img_stats=st)
         else:
             st = None
@@ -413,6 +413,11 @@ class _VAEFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, vae, x, eps, *params):
+        with _host.zero_pool(x.device):
+            return _VAEFn._forward(ctx, vae, x, eps)
+
+    @staticmethod
+    def _forward(ctx, vae, x, eps):
         lib = _capi.lib()
         B = x.shape[0]
         L = vae.latent_dim
@@ -430,6 +435,11 @@ class _VAEFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_recon, d_mu, d_logvar):
+        with _host.zero_pool(ctx.saved_tensors[0].device):
+            return _VAEFn._backward(ctx, d_recon, d_mu, d_logvar)
+
+    @staticmethod
+    def _backward(ctx, d_recon, d_mu, d_logvar):
         lib = _capi.lib()
         vae, esv, dsv = ctx.vae, ctx.esv, ctx.dsv
         enc, dec = vae.encoder, vae.decoder
@@ -446,7 +456,7 @@ class _VAEFn(torch.autograd.Function):
         hw = 128
         dx = torch.empty(B, hw * hw, 32, device=dev, dtype=torch.bfloat16)
         dwf = torch.zeros_like(fc.weight, dtype=torch.float32)
-        dbf = torch.zeros(3, device=dev)
+        dbf = _host.zeros(3, device=dev)
         check(lib.lun_final_conv_bwd(d_recon.data_ptr(), recon.data_ptr(), dsv["x_last"].data_ptr(),
                                      _f32(fc.weight).data_ptr(), dx.data_ptr(), dwf.data_ptr(), dbf.data_ptr(), B, hw,
                                      hw, _stream()), "lun_final_conv_bwd")
@@ -523,7 +533,7 @@ class _VAEFn(torch.autograd.Function):
             g[pre + ".1.weight"], g[pre + ".1.bias"] = dgam, dbet
             if i == 0:
                 dw0 = torch.zeros_like(conv.weight, dtype=torch.float32)
-                db0 = torch.zeros(C, device=dev)
+                db0 = _host.zeros(C, device=dev)
                 check(lib.lun_conv3x3_c3_wgrad(dt0.data_ptr(), x.data_ptr(), dw0.data_ptr(), db0.data_ptr(), B,
                                                x.shape[2], x.shape[3], C, 2, _stream()), "lun_conv3x3_c3_wgrad")
                 g[pre + ".0.weight"], g[pre + ".0.bias"] = dw0, db0
@@ -557,7 +567,7 @@ class _VaeLossFn(torch.autograd.Function):
             mulv = torch.as_strided(mu, (B, 2 * L), (2 * L, 1))     # mu | logvar already packed by the fused fc
         else:
             mulv = torch.cat([mu.float(), logvar.float()], 1).contiguous()
-        sums = torch.zeros(2, device=recon.device, dtype=torch.float32)
+        sums = _host.zeros(2, device=recon.device)
         check(lib.lun_vae_loss_fwd(recon.data_ptr(), images.data_ptr(), mulv.data_ptr(), sums.data_ptr(),
                                    recon.numel(), B, L, _stream()), "lun_vae_loss_fwd")
         ctx.save_for_backward(recon, images, mulv)
