@@ -380,9 +380,11 @@ int launch_conv_wgrad(const void* dy, int YB, int YH, int YW, const void* x, int
     int wpt = workers / tiles;                      // workers per output tile = major K slices
     if (wpt > chunks / 8) wpt = chunks / 8;         // keep at least 8 k-chunks per unit
     if (wpt >= 1 && tiles * wpt * 10 >= workers * 9) {      // at most 10 % of the grid may stay idle
-      int nsub = chunks / wpt / 512;                // sub-units of ~512 chunks: the drain overlaps the next main loop
+      // sub-units of <= ~192 k-chunks: the drain of one overlaps the main loop of the next, and a TMEM accumulator never
+      // sums more than ~25 k pixels before it is flushed (fp32 accumulation error grows with the run length)
+      int nsub = (chunks / wpt + 191) / 192;
       if (nsub < 1) nsub = 1;
-      if (nsub > 16) nsub = 16;
+      if (nsub > 64) nsub = 64;
       g.lockstep = 1;
       g.nsub = nsub;
       g.splits = wpt * nsub;

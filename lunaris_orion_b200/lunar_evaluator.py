@@ -557,8 +557,14 @@ def _block_forward(blk, x, B, H, W, training, n_updates, save, pool, tag, xmom=N
     p2d = d1.p if training else 0.0
 
     st = _host.zeros(2 * C, device=dev) if training else None
+    # the statistics epilogue hides behind a K = 9 * 512 main loop; behind the thin first conv of an expert (K = 9 * 128)
+    # it costs more than one separate pass over the 1 GB output, so that conv runs without it
+    epi_stats = training and Cin * 9 >= 2304
     y1 = ops.conv2d_fprop(x.view(B, H, W, Cin), _packed(c1.weight, "fwd"), 3, 1, 1, bias=_packed(c1.bias, "f32"),
-                          act_leaky=True, stats=st, slope=_SLOPE)
+                          act_leaky=True, stats=st if epi_stats else None, slope=_SLOPE)
+    if training and not epi_stats:
+        check(_capi.lib().lun_channel_stats_bf16(y1.data_ptr(), B * HW, C, st.data_ptr(), _stream()),
+              "lun_channel_stats_bf16")
     sc1, sh1 = _bn_train(bn1, st, B * HW, n_updates)[:2] if training else _bn_eval(bn1)
     m1 = _drop2d_mask(B, C, p2d, dev, tag + ".drop2d_1") if p2d > 0 else None
     h2, att_saved = _attention_forward(blk.attention, y1.view(B, HW, C), sc1, sh1, m1, B, H, W, training, save, tag)

@@ -82,6 +82,14 @@ def test_step_with_dropout_on_matches_oracle_with_injected_masks(cuda_dev, tmp_p
         "--feature_dim", str(feat), "--seed", "42"])
     tm = TrainingManager(args, device=cuda_dev)
     assert tm.teacher.dropout_rate == P
+    # The default init makes the heads ill-conditioned (kaiming-fan_out MLPs on LayerNormed features: logits up to +-17,
+    # saturated sigmoids - SURVEY.md 7 hard part 6): a bf16-sized logit difference then rescales each sample's gradient
+    # by tens of percent. The arithmetic is compared at a well-conditioned point instead: the heads' Linear weights are
+    # shrunk by 10x on both sides (logits of order 1); the ill-conditioned default is what the golden tests run.
+    with torch.no_grad():
+        for n, p_ in tm.teacher.named_parameters():
+            if n.startswith(("gate", "quality_heads", "semantic_head")) and n.endswith("weight") and p_.dim() == 2:
+                p_.mul_(0.1)
     x = tc.images(B, seed=41)
     vsd, tsd = tc.oracle_sd(tm.vae), tc.oracle_sd(tm.teacher)          # pre-step weights and BatchNorm buffers
     vsd_cal, tsd_cal = tc.oracle_sd(tm.vae), tc.oracle_sd(tm.teacher)  # second copy for the bf16 calibration run
@@ -147,32 +155,10 @@ def test_step_with_dropout_on_matches_oracle_with_injected_masks(cuda_dev, tmp_p
         assert abs(m[k] - ref[k]) <= tol, (k, m[k], ref[k], cal[k])
     assert abs(m["advantage"]) < 1e-6 and abs(m["pg_loss"]) < 1e-6
     assert report["recon"][0] <= 3 * report["recon"][1] + 0.01, report["recon"]
-    # VAE gradients (no head in their path on the first step: advantage == 0): elementwise, per tensor within 3x its
-    # own bf16 calibration (+2 % of the tensor's scale)
-    for n in ref_grads:
-        if n.startswith("vae."):
-            assert e_mine[n] <= 3 * e_cal[n] + 0.02, (n, e_mine[n], e_cal[n])
-    # Teacher gradients all pass through d sigmoid(quality logits): the heads are ill-conditioned (kaiming-fan_out
-    # MLPs on LayerNormed features, SURVEY.md 7 hard part 6), so a small logit difference rescales the whole gradient
-    # of an expert (the bf16-autocast oracle itself is 76 % off on gate.2.bias here). Compared scale-free: the DIRECTION
-    # of every tensor (cosine with the oracle's) within 3x the calibration's own angle; the elementwise Teacher check
-    # with dropout on lives in test_trunk_with_dropout_on_matches_oracle_elementwise below, behind the heads.
-    def cosines(get):
-        out = {}
-        for n, rg in ref_grads.items():
-            if n.startswith("teacher.") and not n.endswith("shortcut.0.bias"):
-                g = get(n).flatten().double()
-                r = rg.flatten().double()
-                out[n] = float((g @ r) / (g.norm() * r.norm() + 1e-30))
-        return out
-    c_mine, c_cal = cosines(lambda n: mine[n]), cosines(lambda n: cal_grads[n])
-    report["teacher_grad_cosine_worst_mine"] = sorted(c_mine.items(), key=lambda kv: kv[1])[:6]
-    report["teacher_grad_cosine_worst_cal"] = sorted(c_cal.items(), key=lambda kv: kv[1])[:6]
-    if os.path.isdir(out_dir):
-        json.dump(report, open(os.path.join(out_dir, "dropout_parity_report.json"), "w"), indent=1, default=str)
-    for n in c_mine:
-        assert 1 - c_mine[n] <= 3 * (1 - c_cal[n]) + 0.02, (n, c_mine[n], c_cal[n])
-    assert worst_mine <= 3 * worst_cal + 0.05, (report["grad_worst_mine"], report["grad_worst_cal"])
+    # ALL 72 + 100 gradient tensors elementwise: per tensor within 3x its own bf16 calibration (+2 % of its scale)
+    bad = {n: (e_mine[n], e_cal[n]) for n in ref_grads if e_mine[n] > 3 * e_cal[n] + 0.02}
+    assert not bad, bad
+    assert worst_mine <= 3 * worst_cal + 0.02, (report["grad_worst_mine"], report["grad_worst_cal"])
 
 
 @pytest.mark.gpu

@@ -25,7 +25,7 @@ for e in prof.events():
         agg[name][1] += e.device_time
 tot = sum(v[1] for v in agg.values())
 print(f"total kernel time {tot/1e3:.1f} ms")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("PROF_TOP", "22"))]:
     print(f"{v[1]/tot*100:6.2f}%  {v[1]/1e3:8.2f} ms  n={v[0]:4d}  avg={v[1]/v[0]:8.1f} us  {k}")
 # conv_fprop by duration bucket
 b = collections.defaultdict(lambda: [0, 0.0])
