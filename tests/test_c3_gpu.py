@@ -93,7 +93,7 @@ def test_two_trainer_steps_at_c3_shapes_match_the_reference_trainer(cuda_dev, tm
         for n, p in model.named_parameters():
             if n not in ref0[key] or n.endswith("shortcut.0.bias"):
                 continue
-            d = (tc.fingerprint_k(p, cfg["samples"])["samples"] - ref0[key][n]["samples"]).abs()
+            d = (tc.fingerprint_k(p, ref0[key][n]["samples"].numel())["samples"] - ref0[key][n]["samples"]).abs()
             bad += int((d > 1.0 * lr).sum())
             tot += d.numel()
         flips[name] = bad / tot
