@@ -36,11 +36,12 @@ sys.path.insert(0, ROOT)
 CFG = dict(batch=64, latent=512, emb=256, feat=512)
 GF_PER_IMG = 5443.3   # algorithmic GFLOP per image per step, as-executed, recompute excluded
 GF_PER_IMG_C2 = 1423.0
-PRE_ROLL = 6          # untimed steps on top of --warmup before the first timed loop
+PRE_ROLL_S = 6.0      # untimed steps on top of --warmup: keep stepping until this many seconds have passed
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (3x3 512->512, B=64, production
-# epilogue) from an `ncu --set full` capture of tools/prof_conv.py; not re-measured by this run
-NCU_CAPTURE = {(512, 64): {"traffic": 1.458739e9 + 1.048327e9, "tensor_pipe_active_pct": 95.1,
-                           "file": "profiles/r01b_ncu_conv_fprop_3x3_512_B64.txt"}}
+# epilogue) from the round's `ncu --set full` capture of tools/prof_conv.py (algorithmic bytes: 2.152e9); a constant
+# from that capture, not re-measured by this run
+NCU_CAPTURE = {(512, 64): {"traffic": 1.079173e9 + 1.041929e9, "tensor_pipe_active_pct": 98.1,
+                           "file": "profiles/r02_ncu_conv_fprop_and_wgrad_3x3_512_B64.txt"}}
 
 
 def _peaks():
@@ -195,10 +196,21 @@ def run_ours(a):
         torch.cuda.current_stream().synchronize()
         return float(host_metrics[0])                      # the step's result is read on the host
 
-    # W warm-up steps as asked, plus a fixed pre-roll: the first ~10 steps of a process are 2-3 % slower than the steady
-    # state (allocator pools and the zero-pool still growing, clocks settling under the power cap) - round 1's
-    # "e2e > value" was this drift, the A-B-A loop below now bounds what is left of it
-    for i in range(a.warmup + PRE_ROLL):
+    # W warm-up steps as asked, plus a pre-roll: under the 1000 W cap the SM clock keeps climbing for the first seconds
+    # of a run (median 1492 MHz in a first loop, 1552 MHz in the same loop repeated later), which made the first timed
+    # loop 2-3 % slower than every later one - round 1's "e2e > value". The A-B-A loop below bounds what is left.
+    torch.cuda.synchronize()
+    t_w = time.time()
+    for i in range(a.warmup):
+        step_resident(i)
+    torch.cuda.synchronize()
+    # number of pre-roll steps from rank 0's warm-up timing, the same on every rank (each step holds collectives)
+    per_step = (time.time() - t_w) / a.warmup if a.warmup > 0 else None
+    n_pre = torch.tensor([min(40, max(3, int(PRE_ROLL_S / per_step))) if per_step else 3], device=dev)
+    if world > 1:
+        dist.broadcast(n_pre, 0)
+    pre_roll = int(n_pre.item())
+    for i in range(pre_roll):
         step_resident(i)
     l0 = lib.lun_launch_count()
     ms, clocks = timed(step_resident, a.steps)
@@ -293,7 +305,7 @@ def run_ours(a):
                                % ("C3 high-end" if (B, a.latent, a.emb, a.feat) == (64, 512, 256, 512) else "custom shapes",
                                   B, a.latent, a.emb, a.feat),
                    "global_batch": B * world, "parallelism": "dp%d" % world, "l2": "working set >> 126 MB L2",
-                   "untimed_steps_before_timing": a.warmup + PRE_ROLL},
+                   "untimed_steps_before_timing": a.warmup + pre_roll},
         "e2e": {"value": round(n_img / (ms_e2e / 1e3), 2), "unit": "images/s",
                 "h2d_bytes_per_step": tm.train_loader.h2d_bytes_per_batch, "d2h_bytes_per_step": 48,
                 "ms_per_step": round(ms_e2e / a.steps, 3), "clocks": clocks_e2e,
