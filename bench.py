@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 CFG = dict(batch=64, latent=512, emb=256, feat=512)
 GF_PER_IMG = 5443.3   # algorithmic GFLOP per image per step, as-executed, recompute excluded
 GF_PER_IMG_C2 = 1423.0
-PRE_ROLL_S = 6.0      # untimed steps on top of --warmup: keep stepping until this many seconds have passed
+PRE_ROLL_S = 10.0     # untimed steps on top of --warmup: keep stepping until this many seconds have passed
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (3x3 512->512, B=64, production
 # epilogue) from the round's `ncu --set full` capture of tools/prof_conv.py (algorithmic bytes: 2.152e9); a constant
 # from that capture, not re-measured by this run
@@ -197,20 +197,22 @@ def run_ours(a):
         return float(host_metrics[0])                      # the step's result is read on the host
 
     # W warm-up steps as asked, plus a pre-roll: under the 1000 W cap the SM clock keeps climbing for the first seconds
-    # of a run (median 1492 MHz in a first loop, 1552 MHz in the same loop repeated later), which made the first timed
-    # loop 2-3 % slower than every later one - round 1's "e2e > value". The A-B-A loop below bounds what is left.
-    torch.cuda.synchronize()
-    t_w = time.time()
+    # of a run (medians 1462 -> 1597 -> 1620 MHz over three consecutive 5-step loops of one process), which made the
+    # first timed loop 2-5 % slower than every later one - round 1's "e2e > value". After ~10 s the three loops agree to
+    # 1 % (246.6 / 245.2 / 247.5 images/s); the A-B-A loop below bounds what is left.
     for i in range(a.warmup):
         step_resident(i)
     torch.cuda.synchronize()
-    # number of pre-roll steps from rank 0's warm-up timing, the same on every rank (each step holds collectives)
-    per_step = (time.time() - t_w) / a.warmup if a.warmup > 0 else None
-    n_pre = torch.tensor([min(40, max(3, int(PRE_ROLL_S / per_step))) if per_step else 3], device=dev)
+    t_w = time.time()
+    for i in range(2):                  # two settled steps give the step time (the W warm-up steps include one-off costs)
+        step_resident(i)
+    torch.cuda.synchronize()
+    # number of pre-roll steps from rank 0's timing, the same on every rank (each step holds collectives)
+    n_pre = torch.tensor([min(60, max(3, int(PRE_ROLL_S / max((time.time() - t_w) / 2, 1e-3))))], device=dev)
     if world > 1:
         dist.broadcast(n_pre, 0)
-    pre_roll = int(n_pre.item())
-    for i in range(pre_roll):
+    pre_roll = 2 + int(n_pre.item())
+    for i in range(pre_roll - 2):
         step_resident(i)
     l0 = lib.lun_launch_count()
     ms, clocks = timed(step_resident, a.steps)
