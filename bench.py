@@ -484,8 +484,8 @@ def cpu_reference(a, steps, warmup, batch, budget_s=150.0):
     val = batch * done / t_total
     return {"value": round(val, 4), "unit": "images/s", "cores": cores, "kind": kind, "timed_steps": done,
             "warmup_steps": warmup, "batch": batch,
-            "sample": "%s; %d timed step(s) after %d warm-up on batch %d of the C3 architecture (latent %d, emb %d, feat "
-                      "%d), %d threads, %.1f s/step" % (what, done, warmup, batch, a.latent, a.emb, a.feat,
+            "sample": "%s; %d timed step(s) after %d warm-up on batch %d of the architecture latent %d / emb %d / feat "
+                      "%d, %d threads, %.1f s/step" % (what, done, warmup, batch, a.latent, a.emb, a.feat,
                                                         torch.get_num_threads(), t_total / done)}
 
 
@@ -540,6 +540,8 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if a.ref_config == "c1":        # BASELINE configs[0], the reference's own CPU-runnable case
+        a.latent, a.emb, a.feat, a.cpu_batch, a.eager_batch = 256, 128, 256, 8, 8
     if a.ref_device == "cuda":
         return eager_gpu_reference(a)
     cb = cpu_reference(a, steps=a.steps, warmup=min(a.warmup, 1), batch=a.cpu_batch, budget_s=a.ref_budget)
@@ -548,10 +550,13 @@ def run_reference(a):
         "value": cb["value"], "unit": "images/s", "n_gpus": a.gpus, "steps": cb["timed_steps"],
         "warmup": cb["warmup_steps"], "ms_per_step": round(1e3 * a.cpu_batch / cb["value"], 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3 high-end architecture (latent %d, emb %d, feat %d), reference CPU path on host cores; "
-                               "each step = one full _process_batch on a bounded sample of batch %d (a batch-64 step "
-                               "of the reference takes tens of minutes on CPU; steps stop at a %d s budget)"
-                               % (a.latent, a.emb, a.feat, a.cpu_batch, int(a.ref_budget))},
+        "config": {"workload": ("C1 (BASELINE configs[0]: batch %d, latent %d, emb %d, feat %d), reference CPU path on host "
+                                "cores, full batch; steps stop at a %d s budget"
+                                % (a.cpu_batch, a.latent, a.emb, a.feat, int(a.ref_budget))) if a.ref_config == "c1" else
+                   ("C3 high-end architecture (latent %d, emb %d, feat %d), reference CPU path on host cores; "
+                    "each step = one full _process_batch on a bounded sample of batch %d (a batch-64 step "
+                    "of the reference takes about nine minutes on 16 cores; steps stop at a %d s budget)"
+                    % (a.latent, a.emb, a.feat, a.cpu_batch, int(a.ref_budget)))},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -579,6 +584,9 @@ def main():
     p.add_argument("--ref-device", dest="ref_device", default="cpu", choices=["cpu", "cuda"],
                    help="--impl reference only: 'cuda' times the unmodified reference as stock PyTorch eager kernels on the GPU")
     p.add_argument("--eager-batch", dest="eager_batch", type=int, default=16)
+    p.add_argument("--ref-config", dest="ref_config", default="c3", choices=["c3", "c1"],
+                   help="--impl reference only: c3 = our arm's architecture on a bounded batch (default, what the driver "
+                        "compares); c1 = BASELINE configs[0] at its full batch of 8 (SURVEY.md 8d)")
     a = p.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -17,7 +17,11 @@ __device__ __forceinline__ float mish_tanh_sp(float v, float* e_out) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 20.f) * 1.4426950408889634f));
   *e_out = e;
   const float n = e * (e + 2.f);
-  return __fdividef(n, n + 2.f);
+  // MUFU.RCP directly: n + 2 lies in [2, 2.4e17], so the range guards of __fdividef (FSETP + two predicated FMULs, a
+  // quarter of the instructions of this function) protect nothing here
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.f));
+  return n * r;
 }
 __device__ __forceinline__ float mish_f(float v) {
   float e;
@@ -34,7 +38,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float mish_grad_f(float v) {
   float e;
   const float t = mish_tanh_sp(v, &e);
-  const float sg = __fdividef(e, 1.f + e);      // == 1.0f for v >= 20 (e is clamped at exp(20))
+  float r1;                                     // 1 + e lies in [1, 4.9e8]: plain MUFU.RCP, as above
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(1.f + e));
+  const float sg = e * r1;                      // == 1.0f for v >= 20 (e is clamped at exp(20))
   return t + v * (1.f - t * t) * sg;
 }
 
