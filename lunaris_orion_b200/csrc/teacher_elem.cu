@@ -687,6 +687,10 @@ static int elem_blocks_per_image(int HW, int C, int B) {
   // many more blocks than resident slots so the tail wave is a small fraction of the work
   int want = (148 * 32 + B - 1) / B;
   if (want < 1) want = 1;
+  // ... but a block should still walk >= 8 iterations, or its prologue (channel parameters, reduction epilogue) shows:
+  // at C2 (batch 16, 256 channels) the 32 x SMs rule alone gave blocks of 1.7 iterations
+  const int cap = per >= 8 ? per / 8 : 1;
+  if (want > cap) want = cap;
   return per < want ? per : want;
 }
 static bool chan_ok(int C) { return C % 8 == 0 && C / 8 <= kEThreads && C >= 8; }

@@ -44,6 +44,22 @@ __device__ __forceinline__ float mish_grad_f(float v) {
   return t + v * (1.f - t * t) * sg;
 }
 
+// GroupNorm affine + Mish of one element in 7 instructions (FFMA, MUFU.EX2, FADD, FFMA, MUFU.RCP, FFMA, FMUL). The affine
+// is applied in the log2 domain, a = x * sc2 + sh2 with sc2 = sc * log2(e), sh2 = sh * log2(e), so that a feeds the
+// exponential directly and u = gn(x) = a * ln 2 never has to exist on its own:
+//   e = 2^a = exp(u),  s = 1 + e,  tanh(softplus(u)) = (s^2 - 1) / (s^2 + 1) = 1 - 2 / (s^2 + 1)
+//   mish(u) = a * (ln 2 - 2 ln 2 / (s^2 + 1))
+// No clamp: e = inf gives 1 / inf = 0 and the linear branch u; for u << 0 the factor cancels to an absolute error of
+// ~1e-7, i.e. |u| * 1e-7 on a value that is rounded to bf16 next.
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float gn_mish_elem(float x, float sc2, float sh2) {
+  const float a = fmaf(x, sc2, sh2);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+  const float s = e + 1.f;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(s, s, 1.f)));
+  return a * fmaf(r, -2.f * kLn2, kLn2);
+}
 // ------------------------------------------------------------------------------------------- per-image channel sums
 // stats[b][0][c] = sum_hw x, stats[b][1][c] = sum_hw x^2   (caller zeroes)
 __global__ void __launch_bounds__(kVT) image_channel_stats_kernel(const bf16* __restrict__ x,
@@ -135,19 +151,20 @@ __global__ void __launch_bounds__(kVT) gn_mish_fwd_kernel(const bf16* __restrict
   const float inv_m = 1.f / ((float)cpg * (float)HW);
   block_group_stats(stats + (size_t)b * 2 * C, nullptr, nullptr, C, groups, inv_m, eps, sg);
   if (lane_px >= lanes) return;
-  float sc[8], sh[8];
+  float sc2[8], sh2[8];                              // GroupNorm affine in the log2 domain (gn_mish_elem)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float2 ms = sg[(c0 + j) / cpg];
-    sc[j] = gamma[c0 + j] * ms.y;
-    sh[j] = beta[c0 + j] - ms.x * sc[j];
+    const float sc = gamma[c0 + j] * ms.y;
+    sc2[j] = sc * kLog2e;
+    sh2[j] = (beta[c0 + j] - ms.x * sc) * kLog2e;
   }
   for (int p = blockIdx.x * lanes + lane_px; p < HW; p += gridDim.x * lanes) {
     const size_t off = ((size_t)b * HW + p) * C + c0;
     float v[8];
     load8(x + off, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = mish_f(v[j] * sc[j] + sh[j]);
+    for (int j = 0; j < 8; ++j) v[j] = gn_mish_elem(v[j], sc2[j], sh2[j]);
     if (res) {
       float r[8];
       load8(res + off, r);
@@ -456,56 +473,82 @@ __global__ void __launch_bounds__(256, 3) gn_mish_final_conv_tanh_kernel(
   constexpr int C = 32, HX = kFtW + 2, HY = kFtH + 2;
   extern __shared__ __align__(16) unsigned char tile[];            // [HY][HX] pixels of kFtPitch bytes
   __shared__ float2 sg[64];
+  __shared__ __align__(16) __nv_bfloat16 s_w[9][3][C + 2];         // [tap][output][ci] (+2: outputs 0 / 2 on different banks)
   const int b = blockIdx.z, y0 = blockIdx.y * kFtH, x0 = blockIdx.x * kFtW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tq = lane & 3;
-  const int cpg = C / groups;
-  block_group_stats(stats + (size_t)b * 2 * C, nullptr, nullptr, C, groups, 1.f / ((float)cpg * (float)H * (float)W),
-                    eps, sg);
-  // ---- phase 1: halo tile -> GroupNorm + Mish -> bf16 smem (zeros outside the image = the conv's padding)
+  const int cpg = C / groups, cpg_shift = __ffs(cpg) - 1;      // 32 % groups == 0: channels per group is a power of two
+  // ---- phase 1: halo tile -> GroupNorm + Mish -> bf16 smem (zeros outside the image = the conv's padding).
+  // A thread keeps its channel octet; halo pixel k of the thread = (threadIdx.x >> 2) + 64 k, whose (hy, hx) advance by
+  // (1, 30) with one wrap, so neither the pixel coordinates nor the addresses need a division. ALL ten 16-byte loads of
+  // the thread are issued before anything else: their DRAM latency overlaps the weight staging, the group statistics
+  // and the parameter loads below (with three CTAs per SM there is little else to hide it behind).
+  constexpr int kPix = HX * HY, kSteps = (kPix + 63) / 64;
+  const int c0 = (threadIdx.x & 3) * 8;
+  const int hp0 = threadIdx.x >> 2;
+  const bf16* img = t + (size_t)b * H * W * C + c0;
+  uint4 raw[kSteps];
+  unsigned in_mask = 0;
   {
-    const int c0 = (threadIdx.x & 3) * 8;            // 256 % 4 == 0: a thread keeps its channel octet
-    float sc[8], sh[8];
+    int hp = hp0, hy = hp >= HX ? 1 : 0, hx = hp - hy * HX;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 ms = sg[(c0 + j) / cpg];
-      sc[j] = gamma[c0 + j] * ms.y;
-      sh[j] = beta[c0 + j] - ms.x * sc[j];
-    }
-    constexpr int kTasks = HX * HY * 4, kBatch = 5;   // 16-byte chunks of the halo tile; kBatch loads in flight per thread
-    for (int k0 = 0; k0 * 256 < kTasks; k0 += kBatch) {
-      uint4 raw[kBatch];
-      size_t offs[kBatch];
-      int flags[kBatch];                               // bit 0: inside the image, bit 1: interior pixel of the tile
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int task = threadIdx.x + (k0 + u) * 256;
-        const int px = task >> 2, hy = px / HX, hx = px % HX;
-        const int y = y0 + hy - 1, x = x0 + hx - 1;
-        const bool in = task < kTasks && y >= 0 && y < H && x >= 0 && x < W;
-        offs[u] = (((size_t)b * H + (in ? y : 0)) * W + (in ? x : 0)) * C + c0;
-        flags[u] = (in ? 1 : 0) | ((hy >= 1 && hy <= kFtH && hx >= 1 && hx <= kFtW) ? 2 : 0);
-        raw[u] = in ? ldg16(t + offs[u]) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int task = threadIdx.x + (k0 + u) * 256;
-        if (task >= kTasks) break;
-        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-        if (flags[u] & 1) {
-          float v[8];
-          unpack8(raw[u], v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = mish_f(v[j] * sc[j] + sh[j]);
-          __nv_bfloat162 p2[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          packed = *reinterpret_cast<uint4*>(p2);
-          if (h_out != nullptr && (flags[u] & 2)) *reinterpret_cast<uint4*>(h_out + offs[u]) = packed;
-        }
-        *reinterpret_cast<uint4*>(tile + (task >> 2) * kFtPitch + c0 * 2) = packed;
+    for (int k = 0; k < kSteps; ++k) {
+      const int y = y0 + hy - 1, x = x0 + hx - 1;
+      const bool in = hp < kPix && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+      raw[k] = in ? ldg16(img + (y * W + x) * C) : make_uint4(0u, 0u, 0u, 0u);
+      in_mask |= in ? 1u << k : 0u;
+      hp += 64;
+      hx += 64 - HX;
+      hy += 1;
+      if (hx >= HX) {
+        hx -= HX;
+        hy += 1;
       }
     }
   }
+  for (int i = threadIdx.x; i < 3 * C * 9; i += 256) {             // reference layout [o][ci][kh][kw], read coalesced
+    const int tap = i % 9, oc = i / 9;
+    s_w[tap][oc / C][oc % C] = __float2bfloat16_rn(w[i]);
+  }
+  block_group_stats(stats + (size_t)b * 2 * C, nullptr, nullptr, C, groups, 1.f / ((float)cpg * (float)H * (float)W),
+                    eps, sg);
+  {
+    float sc2[8], sh2[8];                            // GroupNorm affine in the log2 domain (gn_mish_elem)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 ms = sg[(c0 + j) >> cpg_shift];
+      const float sc = gamma[c0 + j] * ms.y;
+      sc2[j] = sc * kLog2e;
+      sh2[j] = (beta[c0 + j] - ms.x * sc) * kLog2e;
+    }
+    unsigned char* sdst = tile + hp0 * kFtPitch + c0 * 2;
+    int hy = hp0 >= HX ? 1 : 0, hx = hp0 - hy * HX;
+#pragma unroll
+    for (int k = 0; k < kSteps; ++k) {
+      uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+      if (in_mask >> k & 1u) {
+        const uint32_t xw[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a0 = gn_mish_elem(__uint_as_float(xw[j] << 16), sc2[2 * j], sh2[2 * j]);
+          const float a1 = gn_mish_elem(__uint_as_float(xw[j] & 0xffff0000u), sc2[2 * j + 1], sh2[2 * j + 1]);
+          const __nv_bfloat162 pb = __floats2bfloat162_rn(a0, a1);
+          ow[j] = *reinterpret_cast<const uint32_t*>(&pb);
+        }
+        packed = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if (h_out != nullptr && hy >= 1 && hy <= kFtH && hx >= 1 && hx <= kFtW)    // interior pixel: kept for the backward
+          *reinterpret_cast<uint4*>(h_out + (size_t)b * H * W * C + c0 + ((y0 + hy - 1) * W + x0 + hx - 1) * C) = packed;
+      }
+      if (k < kSteps - 1 || hp0 + 64 * (kSteps - 1) < kPix) *reinterpret_cast<uint4*>(sdst + k * 64 * kFtPitch) = packed;
+      hx += 64 - HX;
+      hy += 1;
+      if (hx >= HX) {
+        hx -= HX;
+        hy += 1;
+      }
+    }
+  }
+  __syncthreads();                                   // s_w and the halo tile are complete
   // B fragment of (tap, k-half): b0 = W[k = 2t, 2t+1][n = g], b1 = W[k = 2t+8, 2t+9][n = g]; n >= 3 is zero padding
   uint32_t bfrag[9][2][2];
 #pragma unroll
@@ -513,18 +556,9 @@ __global__ void __launch_bounds__(256, 3) gn_mish_final_conv_tanh_kernel(
 #pragma unroll
     for (int kh = 0; kh < 2; ++kh)
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        float w0 = 0.f, w1 = 0.f;
-        if (g < 3) {
-          const int ci = kh * 16 + r * 8 + 2 * tq;
-          w0 = w[(g * 32 + ci) * 9 + tap];          // reference layout [o][ci][kh][kw]
-          w1 = w[(g * 32 + ci + 1) * 9 + tap];
-        }
-        __nv_bfloat162 p = __floats2bfloat162_rn(w0, w1);
-        bfrag[tap][kh][r] = *reinterpret_cast<uint32_t*>(&p);
-      }
+      for (int r = 0; r < 2; ++r)
+        bfrag[tap][kh][r] = g < 3 ? *reinterpret_cast<const uint32_t*>(&s_w[tap][g][kh * 16 + r * 8 + 2 * tq]) : 0u;
   const float b_lo = (2 * tq < 3) ? bias[2 * tq] : 0.f, b_hi = (2 * tq + 1 < 3) ? bias[2 * tq + 1] : 0.f;
-  __syncthreads();
   // ---- phase 2: warp w -> tile rows 2w, 2w+1; per row two 16-pixel M tiles
   const uint32_t tile_base = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
   const int mat = lane >> 3;                                      // ldmatrix.x4: matrix fed by this lane's address
@@ -854,7 +888,10 @@ int lun_gn_mish_final_conv_tanh_fwd(const void* t, const float* stats, const flo
   if (W % kFtW || H % kFtH || 32 % groups) return LUN_E_SHAPE;
   dim3 grid(W / kFtW, H / kFtH, B);
   const int smem = (kFtW + 2) * (kFtH + 2) * kFtPitch;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the opt-in smem size is a per-device function attribute
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(gn_mish_final_conv_tanh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)

@@ -21,7 +21,7 @@ def main():
     x = torch.randn(B, HW, C, device=dev).to(torch.bfloat16)
     idn = torch.randn(B, HW, C, device=dev).to(torch.bfloat16)
     sc = torch.rand(C, device=dev) + 0.5; sh = torch.randn(C, device=dev)
-    m2 = le._drop2d_mask(B, C, 0.1, dev); ls = torch.full((C,), 0.1, device=dev)
+    m2 = le._drop2d_mask(B, C, 0.1, dev, "bench"); ls = torch.full((C,), 0.1, device=dev)
     pool = torch.zeros(B, C, device=dev)
     gb = x.numel() * 2 / 1e9
     ms = timeit(lambda: le._affine(x, B, HW, C, sc, sh, mask2d=m2))
