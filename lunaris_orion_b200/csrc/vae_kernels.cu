@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) final_conv_tanh_fwd_kernel(const bf16* __
 //   h = mish(gn(t))  (bf16, optionally written for the backward)   recon = tanh(conv3x3(h, w) + bias)   NCHW fp32
 // A block owns a 32 x 16 pixel tile of one image: the 34 x 18 halo of the raw transposed-conv output t is normalised and
 // activated on the way into shared memory (80-byte pixel pitch: conflict-free ldmatrix), then each warp runs
-// mma.sync m16n8k16 over 2 rows x 2 sixteen-pixel groups with K = 9 taps x 32 channels, N = 8 (3 used). The
+// mma.sync m16n8k16 over 4 rows x one sixteen-pixel group with K = 9 taps x 32 channels, N = 8 (3 used). The
 // normalised 32-channel tensor (the largest of the decoder) is neither written nor re-read on the sampling path.
 constexpr int kFtW = 32, kFtH = 16, kFtPitch = 80;
 __global__ void __launch_bounds__(256, 3) gn_mish_final_conv_tanh_kernel(
@@ -483,8 +483,11 @@ __global__ void __launch_bounds__(256, 3) gn_mish_final_conv_tanh_kernel(
   // the thread are issued before anything else: their DRAM latency overlaps the weight staging, the group statistics
   // and the parameter loads below (with three CTAs per SM there is little else to hide it behind).
   constexpr int kPix = HX * HY, kSteps = (kPix + 63) / 64;
-  const int c0 = (threadIdx.x & 3) * 8;
-  const int hp0 = threadIdx.x >> 2;
+  // lane -> (pixel lane & 7, channel octet lane >> 3): a quarter-warp's eight 16-byte shared-memory stores then hit eight
+  // different bank groups at the 80-byte pixel pitch ((5 p + c) mod 8 is a permutation in p; with four octets of two
+  // pixels per quarter-warp every store was a 2-way conflict), and the warp still reads 512 contiguous bytes
+  const int c0 = ((threadIdx.x >> 3) & 3) * 8;
+  const int hp0 = (threadIdx.x >> 5) * 8 + (threadIdx.x & 7);
   const bf16* img = t + (size_t)b * H * W * C + c0;
   uint4 raw[kSteps];
   unsigned in_mask = 0;
@@ -559,46 +562,53 @@ __global__ void __launch_bounds__(256, 3) gn_mish_final_conv_tanh_kernel(
       for (int r = 0; r < 2; ++r)
         bfrag[tap][kh][r] = g < 3 ? *reinterpret_cast<const uint32_t*>(&s_w[tap][g][kh * 16 + r * 8 + 2 * tq]) : 0u;
   const float b_lo = (2 * tq < 3) ? bias[2 * tq] : 0.f, b_hi = (2 * tq + 1 < 3) ? bias[2 * tq + 1] : 0.f;
-  // ---- phase 2: warp w -> tile rows 2w, 2w+1; per row two 16-pixel M tiles
+  // ---- phase 2: warp w -> 16-pixel column group cb = w & 1, output rows 4 (w >> 1) .. 4 (w >> 1) + 3. Every A fragment
+  // (halo row, dx shift, channel half) is loaded ONCE and feeds the three output rows it reaches (dy = 0, 1, 2): 36
+  // ldmatrix for 72 MMAs per warp instead of 72 (the kernel is bound by the shared-memory pipe: ncu, L1/TEX 76 %), and
+  // the four rows are four independent accumulator chains instead of one chain of 18 dependent MMAs.
   const uint32_t tile_base = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
   const int mat = lane >> 3;                                      // ldmatrix.x4: matrix fed by this lane's address
   const int lpix = (lane & 7) + ((mat & 1) ? 8 : 0), lch = (mat >> 1) ? 8 : 0;
   const long hw = (long)H * W;
+  const int cb = warp & 1, r0 = (warp >> 1) * 4;
+  float d[4][4];
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int r = warp * 2 + rr;
+  for (int i = 0; i < 4; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
 #pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int hr = 0; hr < 6; ++hr)
 #pragma unroll
-      for (int kh3 = 0; kh3 < 3; ++kh3)
+    for (int kw3 = 0; kw3 < 3; ++kw3) {
+      const uint32_t pix_addr = tile_base + ((r0 + hr) * HX + cb * 16 + kw3 + lpix) * kFtPitch + lch * 2;
 #pragma unroll
-        for (int kw3 = 0; kw3 < 3; ++kw3) {
-          const uint32_t pix_addr = tile_base + ((r + kh3) * HX + cb * 16 + kw3 + lpix) * kFtPitch + lch * 2;
+      for (int kh = 0; kh < 2; ++kh) {
+        uint32_t a[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                     : "r"(pix_addr + kh * 32));
 #pragma unroll
-          for (int kh = 0; kh < 2; ++kh) {
-            uint32_t a[4];
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
-                         : "r"(pix_addr + kh * 32));
-            asm volatile(
-                "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-                "{%0, %1, %2, %3};"
-                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[kh3 * 3 + kw3][kh][0]),
-                  "r"(bfrag[kh3 * 3 + kw3][kh][1]));
-          }
+        for (int kh3 = 0; kh3 < 3; ++kh3) {
+          const int orow = hr - kh3;                 // output row (within the band) whose tap (kh3, kw3) reads halo row hr
+          if (orow < 0 || orow > 3) continue;
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+              "{%0, %1, %2, %3};"
+              : "+f"(d[orow][0]), "+f"(d[orow][1]), "+f"(d[orow][2]), "+f"(d[orow][3])
+              : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[kh3 * 3 + kw3][kh][0]),
+                "r"(bfrag[kh3 * 3 + kw3][kh][1]));
         }
-      // C fragment: d[0], d[1] = (pixel g, outputs 2t, 2t+1); d[2], d[3] = (pixel g+8, same outputs)
-      float* obase = recon + (long)b * 3 * hw + (long)(y0 + r) * W + x0 + cb * 16;
-      if (2 * tq < 3) {
-        obase[(2 * tq) * hw + g] = tanh_fast(rbf(d[0] + b_lo));
-        obase[(2 * tq) * hw + g + 8] = tanh_fast(rbf(d[2] + b_lo));
       }
-      if (2 * tq + 1 < 3) {
-        obase[(2 * tq + 1) * hw + g] = tanh_fast(rbf(d[1] + b_hi));
-        obase[(2 * tq + 1) * hw + g + 8] = tanh_fast(rbf(d[3] + b_hi));
-      }
+    }
+  // C fragment: d[.][0], d[.][1] = (pixel g, outputs 2t, 2t+1); d[.][2], d[.][3] = (pixel g+8, same outputs)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* obase = recon + (long)b * 3 * hw + (long)(y0 + r0 + i) * W + x0 + cb * 16;
+    if (2 * tq < 3) {
+      obase[(2 * tq) * hw + g] = tanh_fast(rbf(d[i][0] + b_lo));
+      obase[(2 * tq) * hw + g + 8] = tanh_fast(rbf(d[i][2] + b_lo));
+    }
+    if (2 * tq + 1 < 3) {
+      obase[(2 * tq + 1) * hw + g] = tanh_fast(rbf(d[i][1] + b_hi));
+      obase[(2 * tq + 1) * hw + g + 8] = tanh_fast(rbf(d[i][3] + b_hi));
     }
   }
 }
@@ -829,7 +839,11 @@ int lun_image_channel_stats_bf16(const void* x, float* stats, int B, int HW, int
 int lun_gn_mish_fwd_bf16(const void* x, const float* stats, const float* gamma, const float* beta, const void* res,
                          const void* add, void* y, int B, int HW, int C, int groups, float eps, void* stream) {
   if (C % 8 || C / 8 > kVT || C % groups) return LUN_E_SHAPE;
-  dim3 grid(vae_blocks(HW, C, B), B);
+  // 40 registers: 6 blocks are resident per SM; ~12 blocks per SM in all keep them resident to the end (the 4 per SM of
+  // vae_blocks left the pass at 57 % of its warp slots: ncu, profiles/r02_ncu_c5_decoder_kernels.txt)
+  const int lanes = kVT / (C / 8);
+  int per = (HW + lanes - 1) / lanes, want = (148 * 12 + B - 1) / B;
+  dim3 grid(per < want ? per : want, B);
   gn_mish_fwd_kernel<<<grid, kVT, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, gamma, beta, (const bf16*)res,
                                                              (const bf16*)add, (bf16*)y, HW, C, groups, eps);
   lun::note_launch(1);
