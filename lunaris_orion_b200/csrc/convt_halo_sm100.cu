@@ -34,6 +34,7 @@ constexpr int kCtHW = kCtTW + 2, kCtHH = kCtTH + 2;        // halo tile
 constexpr int kCtHaloBytes = kCtHW * kCtHH * 128;          // 23040
 constexpr int kCtHaloSlot = 23 * 1024;                     // 1024-byte aligned slot
 constexpr int kCtMaxStages = 6;
+constexpr int kCtStageBytes = 4096;                       // per epilogue warp: 32 pixels x up to 128 contiguous output bytes
 
 struct CtGeom {
   int B, H, W, Cin, Cout;
@@ -82,7 +83,8 @@ convt_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   uint8_t* sW = smem;                                  // [kchunks][nent][Cout][64] resident weights
   uint8_t* sA = sW + kchunks * nent * w_tile;          // ring of halo tiles
-  CtBars* bars = reinterpret_cast<CtBars*>(sA + g.stages * kCtHaloSlot);
+  uint8_t* sOut = sA + g.stages * kCtHaloSlot;         // 8 x 4 KB: per-warp output staging (epilogue)
+  CtBars* bars = reinterpret_cast<CtBars*>(sOut + 8 * kCtStageBytes);
   float* s_bias = reinterpret_cast<float*>(bars + 1);  // [Cout]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,6 +194,9 @@ convt_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int c0 = cpp == 2 ? 32 * half : 0;
     const bool do_stats = g.flags & EPI_STATS;
     const int OW = 2 * g.W, OH = 2 * g.H;
+    constexpr int kPB = (NPH == 4 && cpp == 1) ? 128 : 64;          // contiguous output bytes per thread per store round
+    uint8_t* stg = sOut + ew * kCtStageBytes;
+    typedef __nv_bfloat16 bf16_t;
     int acc = 0;
     uint32_t pacc = 0;
     float s1[32], s2[32];
@@ -238,7 +243,6 @@ convt_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           uint32_t r[32];
           tmem_ld32(taddr + ch * 32, r);
           tmem_ld_wait();
-          const int oh = 2 * gj + (p >> 1), ow = 2 * gi + (p & 1);
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -246,9 +250,39 @@ convt_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             pk[2 * j] = pack_bf16x2(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y);
             pk[2 * j + 1] = pack_bf16x2(__uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
           }
-          uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * OH + oh) * OW + ow) * Cout + c0);
+          // A thread holds 64 contiguous output bytes per chunk (128 when its two chunks are the two horizontal phases of
+          // one output row: NPH = 4, Cout = 32), but neighbouring threads are 128 / 256 bytes apart, so direct 16-byte
+          // stores touched 32 different lines per instruction (ncu: L1/TEX 70 % busy in a kernel that moves 0.4 GB). The
+          // pieces go through a warp-private staging tile (XOR-swizzled: conflict-free both ways) and leave as stores in
+          // which consecutive lanes write consecutive 16-byte pieces.
+          if (kPB == 128) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 * n + j) ^ (lane & 7)) << 4)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          if (kPB == 64 || n == my_n - 1) {
+            __syncwarp();
+            constexpr int G = kPB / 16;                                   // lanes per thread-slot
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+              const int t = k * (32 / G) + lane / G, piece = lane % G;    // slot t = the lane whose pixel this piece belongs to
+              const int tj = th * kCtTH + q * 4 + (t >> 3), ti = tw * kCtTW + (t & 7);
+              const uint4 v = *reinterpret_cast<const uint4*>(
+                  stg + t * kPB + ((kPB == 128 ? (piece ^ (t & 7)) : (piece ^ ((t >> 1) & 3))) << 4));
+              // kPB == 128: pieces 0-3 are phase pw = 0, pieces 4-7 phase pw = 1 of the same output row (oh from p >> 1)
+              const int ow_t = 2 * ti + (kPB == 128 ? 0 : (p & 1));
+              const int oh_t = 2 * tj + (p >> 1);
+              bf16_t* dstp = out + ((static_cast<size_t>(b) * OH + oh_t) * OW + ow_t) * Cout + c0 + piece * 8;
+              *reinterpret_cast<uint4*>(dstp) = v;
+            }
+            __syncwarp();
+          }
           if (do_stats) {
             // statistics of what was stored (bf16-rounded), as GroupNorm sees them
 #pragma unroll
@@ -288,7 +322,7 @@ int lun_convT4x4s2_halo_bf16(const void* x, int B, int H, int W, int Cin, const 
   if (H % kCtTH || W % kCtTW || Cin % 64 || (Cout != 32 && Cout != 64)) return LUN_E_SHAPE;
   const int kchunks = Cin / 64;
   // all four phases per CTA when their 16 slabs fit next to a 4-stage halo ring, otherwise one phase per CTA
-  const int budget = 227 * 1024 - 1024 - (int)sizeof(CtBars) - Cout * 4;
+  const int budget = 227 * 1024 - 1024 - (int)sizeof(CtBars) - Cout * 4 - 8 * kCtStageBytes;
   int nph = 4;
   if (kchunks * 16 * Cout * 128 + 4 * kCtHaloSlot > budget) nph = 1;
   const int nent = nph == 4 ? 16 : 4;
@@ -306,7 +340,7 @@ int lun_convT4x4s2_halo_bf16(const void* x, int B, int H, int W, int Cin, const 
   g.nph = nph;
   g.stages = stages;
   g.flags = (bias ? EPI_BIAS : 0) | (img_stats ? (EPI_STATS | EPI_STATS_IMG) : 0);
-  const int smem = w_bytes + stages * kCtHaloSlot + (int)sizeof(CtBars) + Cout * 4 + 1024;
+  const int smem = w_bytes + stages * kCtHaloSlot + 8 * kCtStageBytes + (int)sizeof(CtBars) + Cout * 4 + 1024;
   static bool configured_dev[64] = {};   // the opt-in smem size is a per-device function attribute
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
