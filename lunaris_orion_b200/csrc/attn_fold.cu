@@ -113,12 +113,19 @@ attn_fold_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, co
   }
   __syncthreads();
 
-  auto issue_chunk = [&](int b, int i, int stage) {   // one whole warp: one row copy per lane
+  // The 32 row copies of a chunk are issued by ALL eight warps, four rows each (lanes 0-3): a bulk copy is a uniform-
+  // datapath instruction, so a warp issues its lanes' copies one after the other (~30 cycles each) - with one warp
+  // issuing all 32 the other seven waited ~1000 cycles per item at the next block barrier (ncu source view: 29 % of all
+  // stall samples sat behind that barrier). Warp 0 arms the barrier; a row may complete before the barrier is armed
+  // (the transaction count goes transiently negative, the phase cannot complete before the arming arrival).
+  auto issue_chunk = [&](int b, int i, int stage) {   // every warp
     const int chunk = i < nc - 1 ? i : nc - 1;
-    if (lane == 0) mbar_expect_tx(&full[stage], 32 * C * 2);
-    __syncwarp();
-    bulk_load(smem_u32(Xs + (stage * 32 + lane) * PITCH), y + ((size_t)b * N + 32 * chunk + lane) * C, C * 2,
-              &full[stage]);
+    if (tid == 0) mbar_expect_tx(&full[stage], 32 * C * 2);
+    if (lane < 4) {
+      const int row = warp * 4 + lane;
+      bulk_load(smem_u32(Xs + (stage * 32 + row) * PITCH), y + ((size_t)b * N + 32 * chunk + row) * C, C * 2,
+                &full[stage]);
+    }
   };
   auto load_q = [&](int b, int i, uint4 (&q)[NQ]) {
 #pragma unroll
@@ -157,8 +164,8 @@ attn_fold_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, co
   {
     int b1 = b, i1 = i;
     advance(b1, i1);
-    if (warp == 0) issue_chunk(b, i, 0);
-    if (warp == 1 && it0 + 1 < it1) issue_chunk(b1, i1, 1);
+    issue_chunk(b, i, 0);
+    if (it0 + 1 < it1) issue_chunk(b1, i1, 1);
   }
   load_q(b, i, qraw);
   int cur_b = -1;
@@ -275,13 +282,12 @@ attn_fold_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, co
       fence_proxy_async();                         // results visible to the bulk store
     }
     __syncthreads();                               // (4) chunk stage, Qs, Sp, Ps and Os[stage] are settled
-    if (warp == 0) {
-      if (lane < 8) {                              // one head row per lane
-        bulk_store(xbar + (((size_t)b * nq_pad + i) * 8 + lane) * C, smem_u32(os + lane * PITCH), C * 2);
-        // Os[stage ^ 1] is rewritten by the next item: its stores (committed one item ago) must have read it
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      }
-    } else if (warp == 1 && item + 2 < it1) {
+    if (lane == 0) {                               // one head row per warp (bulk groups are per thread)
+      bulk_store(xbar + (((size_t)b * nq_pad + i) * 8 + warp) * C, smem_u32(os + warp * PITCH), C * 2);
+      // Os[stage ^ 1] is rewritten by the next item: its stores (committed one item ago) must have read it
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+    if (item + 2 < it1) {
       int b2 = b1, i2 = i1;
       advance(b2, i2);
       issue_chunk(b2, i2, stage);
@@ -289,7 +295,7 @@ attn_fold_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, co
     b = b1;
     i = i1;
   }
-  if (tid < 8) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // out[b, i, :] = drop2d(bn(y[b, qtok(i), :])): the query rows of the as-executed attention with its input affine.
