@@ -281,6 +281,11 @@ def run_ours(a):
     if world == 1 and not a.no_extras:
         extras["c5"] = _bench_c5(tm, dev)
         extras["c2"] = _bench_c2(dev)
+        if (a.feat, B) == (512, 64):
+            try:
+                extras["hbm_passes"] = _bench_hbm_passes(dev, B, a.feat)
+            except Exception as e:                         # pragma: no cover
+                extras["hbm_passes"] = {"error": str(e)[:200]}
 
     if rank != 0:
         return
@@ -393,6 +398,76 @@ def _bench_c5(tm, dev):
             "tensor_frac_of_sustained": round(ips * 1.136e9 / 1e12 / pk["bf16_tflops_sustained"], 4),
             "hbm_frac_of_peak": round(ips * 4.3e6 / 1e9 / pk["hbm_gbs"], 4),
             "model": "1.136 GFLOP and ~4.3 MB of compulsory traffic per image (SURVEY.md 8d); includes torch.randn of z"}
+
+
+def _bench_hbm_passes(dev, B, C):
+    """The bandwidth-bound Teacher passes at the step's shapes ([B,16384,C] bf16), each timed ALONE with CUDA events on
+    the launching stream against the measured copy peak: compulsory bytes (tensors read + written once) / time."""
+    import ctypes
+    import torch
+    from lunaris_orion_b200 import _capi, lunar_evaluator as le
+    lib = _capi.lib()
+    HW = 16384
+    pk = _peaks() or {"hbm_gbs": 6556.2}
+    x, idn, x2 = (torch.randn(B, HW, C, device=dev).to(torch.bfloat16) for _ in range(3))
+    sc = torch.rand(C, device=dev) + 0.5
+    sh = torch.randn(C, device=dev)
+    ls = torch.full((C,), 0.1, device=dev)
+    m2 = (torch.rand(B, C, device=dev) > 0.1).float() * 1.109375
+    pool = torch.zeros(B, C, device=dev)
+    mean, rstd, gamma = torch.zeros(C, device=dev), torch.ones(C, device=dev), torch.ones(C, device=dev)
+    gb = x.numel() * 2 / 1e9
+    s0 = torch.cuda.current_stream().cuda_stream
+
+    def timed(fn, iters=8):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+
+    def put(name, ms, nbytes_gb, what):
+        out[name] = {"ms": round(ms, 4), "gbytes": round(nbytes_gb, 3), "achieved_gbs": round(nbytes_gb / ms * 1e3, 1),
+                     "frac_of_hbm_peak": round(nbytes_gb / ms * 1e3 / pk["hbm_gbs"], 4), "traffic": what}
+    ms = timed(lambda: le._affine(x, B, HW, C, sc, sh, mask2d=m2, ls=ls, identity=idn, pool=pool))
+    put("block_tail_fwd", ms, 3 * gb, "BN apply + Dropout2d + layer scale + residual + leaky_relu + pooling: 2 read, 1 written")
+    t = torch.zeros(2, C, device=dev)
+    dpre, dz, dbias = torch.empty_like(x), torch.empty_like(x), torch.zeros(C, device=dev)
+    ms = timed(lambda: _capi.check(lib.lun_block_bwd_reduce_bf16(
+        x.data_ptr(), None, idn.data_ptr(), x2.data_ptr(), mean.data_ptr(), rstd.data_ptr(), m2.data_ptr(),
+        dpre.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), B, HW, C, ctypes.c_float(0.2), s0), "reduce"))
+    put("block_tail_bwd_reduce", ms, 4 * gb, "3 read, 1 written")
+    ms = timed(lambda: _capi.check(lib.lun_block_bwd_apply_bf16(
+        dpre.data_ptr(), None, None, x2.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), ls.data_ptr(),
+        m2.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), dz.data_ptr(), dbias.data_ptr(), B, HW, C,
+        ctypes.c_float(0.2), ctypes.c_float(0.2), s0), "apply"))
+    put("block_tail_bwd_apply", ms, 3 * gb, "2 read, 1 written")
+    nq = HW // 32 + 31
+    nq_pad = (nq + 7) // 8 * 8
+    qt = torch.randn(B, nq_pad, 8 * C, device=dev).to(torch.bfloat16) * 0.05
+    xbar = torch.empty_like(qt)
+    ms = timed(lambda: _capi.check(lib.lun_attn_fold_rows_bf16(
+        x.data_ptr(), sc.data_ptr(), sh.data_ptr(), m2.data_ptr(), qt.data_ptr(), xbar.data_ptr(), B, HW, C, 8, nq_pad,
+        12345, ctypes.c_float(0.1), s0), "fold"))
+    put("attn_fold", ms, gb + 2 * qt.numel() * 2 / 1e9, "attention input read once + folded queries / outputs")
+    small = torch.zeros(B, nq_pad, C, device=dev, dtype=torch.bfloat16)
+    bias = torch.zeros(C, device=dev)
+    ms = timed(lambda: _capi.check(lib.lun_proj_expand_bf16(
+        small.data_ptr(), bias.data_ptr(), dz.data_ptr(), B, HW, C, nq, nq_pad, 1, ctypes.c_float(0.1), s0), "expand"))
+    put("proj_expand", ms, gb, "write-only stream with one dropout hash per two elements")
+    st = torch.zeros(2 * C, device=dev)
+    ms = timed(lambda: _capi.check(lib.lun_channel_stats_bf16(x.data_ptr(), B * HW, C, st.data_ptr(), s0), "stats"))
+    put("channel_stats", ms, gb, "1 read")
+    out["peak_gbs"] = pk["hbm_gbs"]
+    out["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (torch copy_, read + write bytes)"
+    return out
 
 
 def _bench_c2(dev):

@@ -57,7 +57,11 @@ def test_two_trainer_steps_at_c3_shapes_match_the_reference_trainer(cuda_dev, tm
     q_scale = tc.logit_c(ref0["pass_b"]["quality_scores"]).abs().max().item()
     s_scale = tc.logit_c(ref0["pass_b"]["semantic_score"]).abs().max().item()
     report["heads_step0"] = {"quality_logit_abs": dq, "quality_logit_scale": q_scale, "semantic_logit_abs": dsem,
-                             "semantic_logit_scale": s_scale, "expert_weights_abs": dw}
+                             "semantic_logit_scale": s_scale, "expert_weights_abs": dw,
+                             "semantic_logits_mine": tc.logit_c(pass_b["semantic_score"]).flatten().tolist(),
+                             "semantic_logits_ref": tc.logit_c(ref0["pass_b"]["semantic_score"]).flatten().tolist(),
+                             "quality_logits_mine": tc.logit_c(pass_b["quality_scores"]).flatten().tolist(),
+                             "quality_logits_ref": tc.logit_c(ref0["pass_b"]["quality_scores"]).flatten().tolist()}
     rfp = tc.fingerprint_k(tm._last_recon, cfg["samples"])
     report["recon_samples_rel"] = float((rfp["samples"] - ref0["recon_fp"]["samples"]).abs().max() /
                                         ref0["recon_fp"]["samples"].abs().max())
@@ -108,9 +112,16 @@ def test_two_trainer_steps_at_c3_shapes_match_the_reference_trainer(cuda_dev, tm
     if os.path.isdir(OUT):
         json.dump(report, open(os.path.join(OUT, "c3_parity_report.json"), "w"), indent=1, default=str)
 
-    assert dq <= 0.05 * q_scale + 0.05, report["heads_step0"]
-    assert dsem <= 0.08 * s_scale + 0.05, report["heads_step0"]
+    # Head logits per sample. These MLPs amplify bf16-level feature noise by 1e3-1e4 (SURVEY.md 7 hard part 6), and the
+    # BatchNorm sums behind them are accumulated with atomics, so the SAME build moves a semantic logit by +-0.4 from run
+    # to run (four runs on one box: worst semantic difference 0.62 / 0.84 / 0.92 / 1.38, worst quality difference
+    # 0.41-0.48, on a clamped scale of 12). The bounds sit above that spread; what the logits feed - the batch-mean
+    # rewards - is held tightly below.
+    assert dq <= 0.08 * q_scale + 0.05, report["heads_step0"]
+    assert dsem <= 0.15 * s_scale + 0.05, report["heads_step0"]
     assert dw <= 0.02, report["heads_step0"]
+    for k in ("semantic_reward", "quality_reward", "quality_scores"):
+        assert abs(m0[k] - ref0["metrics"][k]) <= 0.02, (k, m0[k], ref0["metrics"][k])
     assert report["recon_samples_rel"] < 0.05
     assert agree["vae"]["aggregate_l1"] < 0.05 and agree["teacher"]["aggregate_l1"] < 0.10, agree
     # VAE gradients: value, sign and direction on the samples. Teacher gradients all pass through d sigmoid(quality
