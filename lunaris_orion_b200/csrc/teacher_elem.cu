@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(kEThreads, 3) blk_bwd_reduce_kernel(const BlkB
 
 // blk_bwd_reduce_kernel specialised for its common call (stored upstream gradient, block output and dpre all present):
 // mean / rstd / Dropout2d factor of the thread's channel octet in registers, packed sign select, as affine_tail_kernel.
+template <bool HAS_DOUT>   // false: the upstream gradient is the broadcast pooled gradient gpool[b][c] (last block of an expert)
 __global__ void __launch_bounds__(kEThreads, 2) blk_bwd_reduce_fast_kernel(const BlkBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const ChanGeom g(a.C);
@@ -405,12 +406,13 @@ __global__ void __launch_bounds__(kEThreads, 2) blk_bwd_reduce_fast_kernel(const
   const int cgi = threadIdx.x % g.cg, lane_px = threadIdx.x / g.cg;
   const bool active = lane_px < g.lanes;
   const int b = blockIdx.y, c0 = cgi * 8;
-  float mean[8], rstd[8], m2[8];
+  float mean[8], rstd[8], m2[8], gp[HAS_DOUT ? 1 : 8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mean[j] = a.mean[c0 + j];
     rstd[j] = a.rstd[c0 + j];
     m2[j] = a.m2 ? a.m2[(size_t)b * C + c0 + j] : 1.f;
+    if (!HAS_DOUT) gp[j] = a.gpool[(size_t)b * C + c0 + j];
   }
   const float slope = a.slope_out;
   float acc[2][8] = {};
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(kEThreads, 2) blk_bwd_reduce_fast_kernel(const
         const int p = p0 + u * g.lanes;
         if (p < a.HW) {
           const size_t off = ((size_t)b * a.HW + p) * C + c0;
-          dr[u] = ldg16(a.dout + off);
+          if (HAS_DOUT) dr[u] = ldg16(a.dout + off);
           orr[u] = ldg16(a.out + off);
           ar[u] = ldg16(a.a + off);
         }
@@ -432,12 +434,15 @@ __global__ void __launch_bounds__(kEThreads, 2) blk_bwd_reduce_fast_kernel(const
         const int p = p0 + u * g.lanes;
         if (p >= a.HW) continue;
         const size_t off = ((size_t)b * a.HW + p) * C + c0;
-        const uint32_t dw[4] = {dr[u].x, dr[u].y, dr[u].z, dr[u].w}, ow_[4] = {orr[u].x, orr[u].y, orr[u].z, orr[u].w};
+        const uint32_t dw[4] = {HAS_DOUT ? dr[u].x : 0u, HAS_DOUT ? dr[u].y : 0u, HAS_DOUT ? dr[u].z : 0u,
+                                HAS_DOUT ? dr[u].w : 0u};
+        const uint32_t ow_[4] = {orr[u].x, orr[u].y, orr[u].z, orr[u].w};
         const uint32_t aw[4] = {ar[u].x, ar[u].y, ar[u].z, ar[u].w};
         uint32_t pw[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float d0 = __uint_as_float(dw[j] << 16), d1 = __uint_as_float(dw[j] & 0xffff0000u);
+          float d0 = HAS_DOUT ? __uint_as_float(dw[j] << 16) : gp[HAS_DOUT ? 0 : 2 * j];
+          float d1 = HAS_DOUT ? __uint_as_float(dw[j] & 0xffff0000u) : gp[HAS_DOUT ? 0 : 2 * j + 1];
           const float o0 = __uint_as_float(ow_[j] << 16), o1 = __uint_as_float(ow_[j] & 0xffff0000u);
           d0 = o0 > 0.f ? d0 : d0 * slope;
           d1 = o1 > 0.f ? d1 : d1 * slope;
@@ -898,7 +903,9 @@ int lun_block_bwd_reduce_bf16(const void* dout, const float* gpool, const void* 
   const int lanes = kEThreads / (C / 8);
   dim3 grid(elem_blocks_per_image(HW, C, B), B);
   if (dout && out && dpre)
-    blk_bwd_reduce_fast_kernel<<<grid, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(a);
+    blk_bwd_reduce_fast_kernel<true><<<grid, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(a);
+  else if (!dout && gpool && out && dpre)
+    blk_bwd_reduce_fast_kernel<false><<<grid, kEThreads, lanes * 2 * C * sizeof(float), (cudaStream_t)stream>>>(a);
   else
     blk_bwd_reduce_kernel<<<grid, kEThreads, (4 * C + lanes * 2 * C) * sizeof(float), (cudaStream_t)stream>>>(a);
   lun::note_launch(1);

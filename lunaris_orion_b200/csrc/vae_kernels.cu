@@ -222,15 +222,20 @@ __global__ void __launch_bounds__(kVT) gn_mish_bwd_kernel(const bf16* __restrict
     for (int p = blockIdx.x * lanes + lane_px; p < HW; p += gridDim.x * lanes) {
       const size_t off = ((size_t)b * HW + p) * C + c0;
       float d[8], xv[8], r[8], dr[8];
-      load8(dy + off, d);
+      // every stream's 16-byte vector is requested before the first is unpacked (up to four loads in flight)
+      const uint4 q_d = ldg16(dy + off), q_x = ldg16(x + off);
+      uint4 q_d2 = make_uint4(0u, 0u, 0u, 0u), q_r = make_uint4(0u, 0u, 0u, 0u);
+      if (dy2) q_d2 = ldg16(dy2 + off);
+      if (res) q_r = ldg16(res + off);
+      unpack8(q_d, d);
       if (dy2) {
         float d2[8];
-        load8(dy2 + off, d2);
+        unpack8(q_d2, d2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] += d2[j];
       }
-      load8(x + off, xv);
-      if (res) load8(res + off, r);
+      unpack8(q_x, xv);
+      if (res) unpack8(q_r, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = (xv[j] - mean[j]) * rstd[j];
