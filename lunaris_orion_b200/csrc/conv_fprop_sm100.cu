@@ -332,8 +332,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               asm volatile(
                   "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                       &tmO),
-                  "r"(stg_base), "r"(g.o_coff + nb), "r"(tw * g.TW + sub_w0), "r"(th * g.TH + sub_h0),
-                  "r"(tb * g.TB + sub_b0)
+                  "r"(stg_base), "r"(g.o_coff + nb), "r"((tw * g.TW + sub_w0) * g.o_mul + o_pw),
+                  "r"((th * g.TH + sub_h0) * g.o_mul + o_ph), "r"(tb * g.TB + sub_b0)
                   : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -557,6 +557,7 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
     const char* e = getenv("LUN_CONV_PAIR");
     pair_mode = e ? atoi(e) : 1;
   }
+  // (pairs for 128-wide N blocks were measured on the 256->128 transposed conv: 93.8 vs 93.0 us, not kept)
   const int cg = (pair_mode && g.block_n == 256 && m_tiles % 2 == 0 && sms % 2 == 0 &&
                   (long)m_tiles / 2 * (g.Cout / g.block_n) * g.nphase >= sms / 2) ? 2 : 1;
   // A-tile reuse: taps sorted by (dy, dx) come in runs of 3 with equal dy and consecutive dx, one image row per tile
@@ -588,7 +589,8 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
     }
     if (col_mode || (g.flags & EPI_DROP_SUM)) g.flags |= EPI_COL_STATS;    // the masked sum only exists on this path
   }
-  if (!(g.flags & EPI_OUT_F32) && g.o_mul == 1)
+  // (a transposed-conv phase writes every other pixel of every other row: the same box with element strides 2)
+  if (!(g.flags & EPI_OUT_F32) && (g.o_mul == 1 || g.o_mul == 2))
     g.flags |= EPI_TMA_STORE;
   else
     g.flags &= ~EPI_TMA_STORE;
@@ -608,7 +610,8 @@ int launch_conv_fprop(const void* x, int XB, int XH, int XW, const void* wpk, in
     const int sub_h = g.TH < 32 / sub_w ? g.TH : 32 / sub_w;
     const int sub_b = 32 / (sub_w * sub_h);
     if (sub_b > g.TB) return 5;
-    rc = make_tmap_nhwc_ex(&tmO, out, g.GB, g.OH, g.OW, g.ldo, 32, sub_w, sub_h, sub_b, 1, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_tmap_nhwc_ex(&tmO, out, g.GB, g.OH, g.OW, g.ldo, 32, sub_w * g.o_mul, sub_h * g.o_mul, sub_b, g.o_mul,
+                           CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   } else {
     tmO = tmA;
