@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel share of the summed device time.
-(cold-cache, serialised times: compare SHARES, not absolutes)    python tools/summarize_launches.py launches.csv"""
+(cold-cache, serialised times: compare SHARES, not absolutes)\n    python tools/summarize_launches.py launches.csv [--from-last KERNEL_NAME_SUBSTRING]"""
 import collections
 import csv
 import gzip
@@ -11,6 +11,13 @@ f = gzip.open(path, "rt") if path.endswith(".gz") else open(path)
 rows = [r for r in csv.reader(l for l in f if l.startswith('"'))]
 hdr = rows[0]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+if len(sys.argv) > 3 and sys.argv[2] == "--from-last":
+    # keep the launches from the LAST occurrence of a kernel on: a capture of N steps cut down to its last whole step
+    # (every step starts with the VAE's first convolution, conv3x3_c3_fwd_kernel)
+    idx = [i for i, r in enumerate(rows) if i > 0 and sys.argv[3] in r[ki]]
+    if idx:
+        print(f"# launches {idx[-1]}..{len(rows) - 1} of {len(rows) - 1} (from the last {sys.argv[3]})")
+        rows = [hdr] + rows[idx[-1]:]
 tot = collections.Counter()
 cnt = collections.Counter()
 for r in rows[1:]:
