@@ -1,4 +1,4 @@
-"""attn_fold at C3 / C2 shapes, CUDA events (LUN_FOLD_PF etc. are read once per process)."""
+"""attn_fold (the as-executed Teacher attention without K / V) at C3 / C2 shapes, CUDA events."""
 import os, sys, ctypes
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -25,7 +25,7 @@ def run(B, C, N=16384):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
     gb = (y.numel() + qt.numel() + xbar.numel()) * 2 / 1e9
-    print(f"attn_fold B={B} C={C}: {ms*1e3:.1f} us  {gb/ms:.2f} TB/s  (LUN_FOLD_PF={os.environ.get('LUN_FOLD_PF','-')})")
+    print(f"attn_fold B={B} C={C}: {ms*1e3:.1f} us  {gb/ms:.2f} TB/s")
     return float(xbar.float().abs().sum())
 
 run(64, 512); run(16, 256)
