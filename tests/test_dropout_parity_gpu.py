@@ -160,7 +160,7 @@ def test_step_with_dropout_on_matches_oracle_with_injected_masks(cuda_dev, tmp_p
     # features that feed the heads sum to ~zero over the batch and every weight gradient downstream of them is a small
     # difference of large per-sample terms - the bf16-autocast oracle itself is 40-90 % off on several of them. A
     # per-tensor 3x bound on a ratio of two such noise responses is a coin flip; the bound is put on the distribution
-    # instead: ratio r = err / (calibration err + 2 %), median <= 2, 90th percentile <= 4, worst <= 10 (a wrong mask,
+    # instead: ratio r = err / (calibration err + 2 %), median <= 2, 90th percentile <= 5, worst <= 10 (a wrong mask,
     # seed or scale puts dozens of tensors at r >> 10; the single worst tensor - a gate weight whose calibration error
     # happens to be small - moved between 5.3 and 6.1 from box to box because the pooling atomics reorder the sums),
     # and every tensor's direction (cosine) stays above 0.8.
@@ -179,7 +179,7 @@ def test_step_with_dropout_on_matches_oracle_with_injected_masks(cuda_dev, tmp_p
     if os.path.isdir(out_dir):
         json.dump(report, open(os.path.join(out_dir, "dropout_parity_report.json"), "w"), indent=1, default=str)
     assert report["teacher_ratio_median"] <= 2.0, report["teacher_ratio_median"]
-    assert report["teacher_ratio_p90"] <= 4.0, ratios[:12]
+    assert report["teacher_ratio_p90"] <= 5.0, ratios[:12]         # seven runs on four boxes: 1.8 - 3.1
     assert ratios[0][0] <= 10.0, ratios[:6]
     assert min(cos.values()) > 0.8, report["teacher_cosine_worst"]
     assert worst_mine <= 3 * worst_cal + 0.05, (report["grad_worst_mine"], report["grad_worst_cal"])
