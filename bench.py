@@ -40,8 +40,8 @@ PRE_ROLL_S = 10.0     # untimed steps on top of --warmup: keep stepping until th
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (3x3 512->512, B=64, production
 # epilogue) from the round's `ncu --set full` capture of tools/prof_conv.py (algorithmic bytes: 2.152e9); a constant
 # from that capture, not re-measured by this run
-NCU_CAPTURE = {(512, 64): {"traffic": 1.079173e9 + 1.041929e9, "tensor_pipe_active_pct": 98.1,
-                           "file": "profiles/r02_ncu_conv_fprop_and_wgrad_3x3_512_B64.txt"}}
+NCU_CAPTURE = {(512, 64): {"traffic": 1.114875e9 + 1.045206e9, "tensor_pipe_active_pct": 97.2,
+                           "file": "profiles/r02c_ncu_conv_fprop_and_wgrad_3x3_512_B64.txt"}}
 
 
 def _peaks():
