@@ -5,11 +5,12 @@ from lunaris_orion_b200.lunar_generate import LunarisCoreVAE
 dev = torch.device("cuda:0")
 torch.manual_seed(42)
 vae = LunarisCoreVAE(512).to(dev).eval()
-for _ in range(3): vae.sample(256)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+for _ in range(3): vae.sample(N)
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    vae.sample(256); torch.cuda.synchronize()
+    vae.sample(N); torch.cuda.synchronize()
 ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
 for e in ev:
     print(f"{e.device_time:8.1f} us  {re.sub(r'\(.*','',e.name)[:60]}")
