@@ -47,14 +47,13 @@ def _ref_apply(dpre, gpool, out, a, mean, rstd, gamma, ls, m2, t1, t2, slope_out
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("C", [64, 192])
+@pytest.mark.parametrize("C,B,HW", [(64, 3, 1000), (192, 3, 1000), (512, 4, 16384)])   # ragged small cases + the C3 shape
 @pytest.mark.parametrize("variant", ["dout", "gpool", "dout_no_out", "gpool_no_dpre", "dout_no_mask_no_ls"])
-def test_block_tail_backward_variants_match_fp32_restatement(cuda_dev, C, variant):
+def test_block_tail_backward_variants_match_fp32_restatement(cuda_dev, C, B, HW, variant):
     from lunaris_orion_b200 import _capi
     lib = _capi.lib()
     dev = cuda_dev
     torch.manual_seed(7)
-    B, HW = 3, 1000                                   # ragged against every block / unroll width
     a = torch.randn(B, HW, C, device=dev).to(torch.bfloat16)
     out = torch.randn(B, HW, C, device=dev).to(torch.bfloat16)
     dout = (torch.randn(B, HW, C, device=dev) * 0.1).to(torch.bfloat16)
