@@ -179,3 +179,21 @@ def test_transposed_conv_delta_filter_is_an_exact_phase_shift(cuda_dev, cin, hw,
     finally:
         ops._HALO_CONVT = saved
     assert (a - b).abs().max().item() <= 2.0 ** -7 * b.abs().max().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,C", [(1000, 64), (4099, 192), (65536 + 17, 512), (7, 8)])
+def test_channel_stats_match_fp64_sums_at_ragged_sizes(cuda_dev, P, C):
+    """lun_channel_stats_bf16 (BatchNorm batch statistics of a bf16 [P, C] tensor; reference lunar_evaluator.py:244,251
+    through nn.BatchNorm2d): sum and sum of squares per channel against fp64, with P ragged against every block, lane
+    and unroll width of the kernel (the four loads of an iteration are predicated one by one)."""
+    from lunaris_orion_b200 import _capi
+    torch.manual_seed(P + C)
+    x = (torch.randn(P, C, device=cuda_dev) * 2 + 0.5).to(torch.bfloat16)
+    st = torch.zeros(2 * C, device=cuda_dev)
+    _capi.check(_capi.lib().lun_channel_stats_bf16(x.data_ptr(), P, C, st.data_ptr(), _capi.raw_stream()),
+                "lun_channel_stats_bf16")
+    xd = x.double()
+    s1, s2 = xd.sum(0), (xd * xd).sum(0)
+    assert (st[:C].double() - s1).abs().max().item() <= 1e-5 * xd.abs().sum(0).max().item() + 1e-4
+    assert (st[C:].double() - s2).abs().max().item() <= 1e-5 * s2.max().item() + 1e-4
