@@ -252,3 +252,36 @@ def test_fused_decoder_tail_equals_the_two_kernels_it_replaces(cuda_dev):
     ref = torch.tanh(torch.nn.functional.conv2d(h_two.float().view(B, H, H, 32).permute(0, 3, 1, 2),
                                                 w.to(torch.bfloat16).float(), bias, padding=1))
     assert (r_fused - ref).abs().max().item() < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,groups,HW", [(32, 8, 1024), (64, 8, 300), (256, 8, 64)])
+def test_gn_mish_forward_matches_torch_fp32_to_a_bf16_ulp(cuda_dev, C, groups, HW):
+    """GroupNorm(8) + Mish (lunar_generate.py:37-38, 96-97, 170-189) through lun_image_channel_stats_bf16 +
+    lun_gn_mish_fwd_bf16 against torch's fp32 group_norm + mish on the same bf16 input, over a wide input range
+    (|x| up to 40: the log2-domain Mish has no clamp - exp overflow must give the linear branch, large negative inputs
+    zero). Bound: two bf16 ulps of the fp32 result."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from lunaris_orion_b200 import _capi
+    lib = _capi.lib()
+    torch.manual_seed(C + HW)
+    B = 3
+    x = torch.randn(B, HW, C, device=cuda_dev) * 3
+    x[0, :7, :5] = 40.0
+    x[1, 3:9, 1:4] = -40.0
+    x = x.to(torch.bfloat16)
+    gamma = torch.rand(C, device=cuda_dev) * 4 + 0.5          # large gains push gn(x) far into both tails
+    beta = torch.randn(C, device=cuda_dev)
+    st = torch.zeros(B, 2, C, device=cuda_dev)
+    s = _capi.raw_stream()
+    _capi.check(lib.lun_image_channel_stats_bf16(x.data_ptr(), st.data_ptr(), B, HW, C, s), "stats")
+    y = torch.empty_like(x)
+    _capi.check(lib.lun_gn_mish_fwd_bf16(x.data_ptr(), st.data_ptr(), gamma.data_ptr(), beta.data_ptr(), None, None,
+                                         y.data_ptr(), B, HW, C, groups, ctypes.c_float(1e-5), s), "gn_mish")
+    xr = x.float().permute(0, 2, 1).reshape(B, C, HW, 1)
+    ref = F.mish(F.group_norm(xr, groups, gamma, beta, 1e-5)).reshape(B, C, HW).permute(0, 2, 1)
+    err = (y.float() - ref).abs()
+    assert torch.isfinite(y.float()).all()
+    assert bool((err <= 2.0 ** -7 * ref.abs() + 2e-6).all()), (err.max().item(), ref.abs().max().item())
