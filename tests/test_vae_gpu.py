@@ -285,3 +285,40 @@ def test_gn_mish_forward_matches_torch_fp32_to_a_bf16_ulp(cuda_dev, C, groups, H
     err = (y.float() - ref).abs()
     assert torch.isfinite(y.float()).all()
     assert bool((err <= 2.0 ** -7 * ref.abs() + 2e-6).all()), (err.max().item(), ref.abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H", [32, 64, 128])
+def test_decoder_tail_matches_torch_fp32_restatement(cuda_dev, H):
+    """up4's GroupNorm + Mish, final_conv and tanh (lunar_generate.py:187-189, 226-228) in the one fused launch against
+    torch: group_norm + mish in fp32, rounded to bf16 (what the kernel stages), conv2d with bf16-rounded weights in fp32,
+    bias, bf16 rounding of the pre-activation, tanh. Whole images, so every border / corner tile (zero padding) and
+    every interior tile boundary (halo exchange) is covered; the normalised tensor written for the backward must be
+    the bf16 rounding of the fp32 result to two ulps."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from lunaris_orion_b200 import _capi
+    lib = _capi.lib()
+    torch.manual_seed(H)
+    B, C = 2, 32
+    t = (torch.randn(B, H * H, C, device=cuda_dev) * 1.5).to(torch.bfloat16)
+    gamma = torch.rand(C, device=cuda_dev) + 0.5
+    beta = torch.randn(C, device=cuda_dev) * 0.1
+    w = torch.randn(3, C, 3, 3, device=cuda_dev) * 0.1
+    bias = torch.randn(3, device=cuda_dev) * 0.1
+    st = torch.zeros(B, 2, C, device=cuda_dev)
+    s = _capi.raw_stream()
+    _capi.check(lib.lun_image_channel_stats_bf16(t.data_ptr(), st.data_ptr(), B, H * H, C, s), "stats")
+    h = torch.empty_like(t)
+    recon = torch.empty(B, 3, H, H, device=cuda_dev)
+    _capi.check(lib.lun_gn_mish_final_conv_tanh_fwd(t.data_ptr(), st.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                    w.data_ptr(), bias.data_ptr(), h.data_ptr(), recon.data_ptr(), B, H, H,
+                                                    8, ctypes.c_float(1e-5), s), "fused tail")
+    x = t.float().view(B, H, H, C).permute(0, 3, 1, 2)
+    h_ref = F.mish(F.group_norm(x, 8, gamma, beta, 1e-5))
+    h_got = h.float().view(B, H, H, C).permute(0, 3, 1, 2)
+    assert bool(((h_got - h_ref).abs() <= 2.0 ** -7 * h_ref.abs() + 2e-6).all())
+    pre = F.conv2d(h_got, w.to(torch.bfloat16).float(), bias, padding=1)       # from what the kernel staged: isolates the conv
+    ref = torch.tanh(pre.to(torch.bfloat16).float())
+    assert (recon - ref).abs().max().item() < 2.0 ** -7, (recon - ref).abs().max().item()
